@@ -1,0 +1,136 @@
+// extern "C" surface of libgenconvit_b200.so (declared in include/genconvit_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace gcv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return GCV_ERR_CUDA;
+  }
+  return GCV_OK;
+}
+
+bool tcgen05_eligible(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t K);
+int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M, int64_t N,
+                 int64_t K, const gcv_epilogue* ep, int force_block_n, cudaStream_t stream);
+int gemm_simt(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M, int64_t N,
+              int64_t K, const gcv_epilogue* ep, cudaStream_t stream);
+int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
+               const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream);
+int ln_patchify2(int dtype, const void* x, void* a, const float* w, const float* b, float eps, int B, int H, int W, int C,
+                 cudaStream_t stream);
+int stem_patchify(int dtype, bool nchw, const void* x, void* a, int B, int H, int W, cudaStream_t stream);
+int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
+                   cudaStream_t stream);
+int pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int B, int HW, int C,
+            cudaStream_t stream);
+int conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b, int stride, int act, int pool,
+                  int B, int H, int W, cudaStream_t stream);
+int im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, cudaStream_t stream);
+int maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t stream);
+int resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* mean_out, int32_t* cls_out,
+                 float* val_out, cudaStream_t stream);
+
+}  // namespace gcv
+
+using namespace gcv;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int gcv_abi_version(void) { return GCV_ABI_VERSION; }
+const char* gcv_last_error(void) { return g_err; }
+
+int gcv_device_supported(int device) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M,
+             int64_t N, int64_t K, const gcv_epilogue* ep, void* stream) {
+  if (!A || !B || !D || !ep) {
+    set_error("gcv_gemm: null pointer");
+    return GCV_ERR_BAD_ARG;
+  }
+  int force_bn = 0;
+  if (backend >= 1000) {              // test hook: 1000 + block_n forces the tcgen05 tile width
+    force_bn = backend - 1000;
+    backend = GCV_GEMM_TCGEN05;
+  }
+  if (backend == GCV_GEMM_AUTO) backend = tcgen05_eligible(dtype, A, lda, B, ldb, K) ? GCV_GEMM_TCGEN05 : GCV_GEMM_SIMT;
+  if (backend == GCV_GEMM_TCGEN05) {
+    if (dtype == GCV_F32) {
+      set_error("gcv_gemm: the tcgen05 back end takes bf16/fp16 operands");
+      return GCV_ERR_UNSUPPORTED;
+    }
+    return gemm_tcgen05(dtype, A, lda, B, ldb, D, M, N, K, ep, force_bn, S(stream));
+  }
+  if (backend == GCV_GEMM_SIMT) return gemm_simt(dtype, A, lda, B, ldb, D, M, N, K, ep, S(stream));
+  set_error("gcv_gemm: unknown backend %d", backend);
+  return GCV_ERR_BAD_ARG;
+}
+
+int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
+                   const float* ln_b, float eps, int B, int H, int W, int C, void* stream) {
+  return dwconv7_ln(dtype, x, y, taps, bias, ln_w, ln_b, eps, B, H, W, C, S(stream));
+}
+int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps, int B, int H,
+                     int W, int C, void* stream) {
+  return ln_patchify2(dtype, x, a, ln_w, ln_b, eps, B, H, W, C, S(stream));
+}
+int gcv_stem_patchify_nchw(int dtype, const float* x, void* a, int B, int H, int W, void* stream) {
+  return stem_patchify(dtype, true, x, a, B, H, W, S(stream));
+}
+int gcv_stem_patchify_nhwc(int dtype, const void* x, void* a, int B, int H, int W, void* stream) {
+  return stem_patchify(dtype, false, x, a, B, H, W, S(stream));
+}
+int gcv_layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
+                       void* stream) {
+  return layernorm_rows(dtype, x, y, w, b, eps, rows, C, S(stream));
+}
+int gcv_pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int B, int HW, int C,
+                void* stream) {
+  return pool_ln(dtype, x, y, w, b, eps, B, HW, C, S(stream));
+}
+int gcv_conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b, int stride, int act, int pool,
+                      int B, int H, int W, void* stream) {
+  return conv3x3_first(dtype, x, y, w, b, stride, act, pool, B, H, W, S(stream));
+}
+int gcv_im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, void* stream) {
+  return im2col3x3(dtype, x, a, B, H, W, C, stride, S(stream));
+}
+int gcv_maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  return maxpool2(dtype, x, y, B, H, W, C, S(stream));
+}
+int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream) {
+  return resize2x_to_nchw(dtype, x, y, B, H, W, C, S(stream));
+}
+int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream) {
+  return nhwc_to_nchw_f32(dtype, x, y, B, H, W, C, S(stream));
+}
+int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video, float* mean_out,
+                     int32_t* cls_out, float* val_out, void* stream) {
+  return score_videos(logits, n_nets, n_frames, frames_per_video, mean_out, cls_out, val_out, S(stream));
+}
+
+}  // extern "C"

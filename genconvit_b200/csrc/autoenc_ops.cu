@@ -1,0 +1,290 @@
+// Autoencoder / VAE side kernels and the scoring kernel.
+//   reference model/genconvit_ed.py:13-33 (Encoder), model/genconvit_vae.py:15-31 (Encoder.features),
+//   model/genconvit_vae.py:105,116 (Resize of the returned x_hat), model/pred_func.py:111-131 (scoring).
+#include "common.cuh"
+
+namespace gcv {
+
+namespace {
+
+template <typename F>
+int dispatch(int dtype, F&& f) {
+  switch (dtype) {
+    case GCV_F32: return f(float{});
+    case GCV_BF16: return f(__nv_bfloat16{});
+    case GCV_F16: return f(__half{});
+    default: set_error("bad dtype %d", dtype); return GCV_ERR_BAD_ARG;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// First 3x3 conv, 3 -> 16 channels, pad 1, straight from NCHW fp32 frames.
+// One thread per output pixel (after pooling when POOL): K = 27 is far too thin for
+// the tensor cores, so this is a direct fp32 conv with the 432 weights broadcast
+// from shared memory.  Output NHWC, 16 channels = two 16-byte stores (16-bit T).
+// ---------------------------------------------------------------------------------
+template <typename T, int STRIDE, bool POOL>
+__global__ void __launch_bounds__(128)
+conv3x3_first_kernel(const float* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
+                     const float* __restrict__ bias, int act, int B, int H, int W, int Ho, int Wo) {
+  __shared__ __align__(16) float ws[27][16];   // [ci*9 + kh*3 + kw][co]
+  __shared__ float bs[16];
+  for (int i = threadIdx.x; i < 432; i += blockDim.x) {
+    const int co = i / 27, r = i - co * 27;      // OIHW: w[co][ci][kh][kw]
+    ws[r][co] = w[i];
+  }
+  if (threadIdx.x < 16) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo);
+  const int64_t t = idx / Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t b = t / Ho;
+  constexpr int NP = POOL ? 2 : 1;          // conv outputs per dim feeding this thread's output
+  constexpr int IN = (NP - 1) * STRIDE + 3; // input patch edge
+  const int cy0 = ho * NP * STRIDE - 1, cx0 = wo * NP * STRIDE - 1;
+  float patch[3][IN][IN];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < IN; ++i)
+#pragma unroll
+      for (int j = 0; j < IN; ++j) {
+        const int yy = cy0 + i, xx = cx0 + j;
+        patch[c][i][j] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((b * 3 + c) * H + yy) * (int64_t)W + xx) : 0.0f;
+      }
+  // all NP*NP conv positions advance together so each tap's 16 weights are read once
+  float acc[NP * NP][16];
+#pragma unroll
+  for (int q = 0; q < NP * NP; ++q)
+#pragma unroll
+    for (int co = 0; co < 16; ++co) acc[q][co] = bs[co];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float wr[16];
+#pragma unroll
+        for (int co = 0; co < 16; co += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[c * 9 + kh * 3 + kw][co]);
+          wr[co] = w4.x; wr[co + 1] = w4.y; wr[co + 2] = w4.z; wr[co + 3] = w4.w;
+        }
+#pragma unroll
+        for (int py = 0; py < NP; ++py)
+#pragma unroll
+          for (int px = 0; px < NP; ++px) {
+            const float v = patch[c][py * STRIDE + kh][px * STRIDE + kw];
+#pragma unroll
+            for (int co = 0; co < 16; ++co) acc[py * NP + px][co] = fmaf(v, wr[co], acc[py * NP + px][co]);
+          }
+      }
+  float out[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    float m = apply_act(acc[0][co], act);
+#pragma unroll
+    for (int q = 1; q < NP * NP; ++q) m = fmaxf(m, apply_act(acc[q][co], act));
+    out[co] = m;
+  }
+  T* dst = y + idx * 16;
+  store8<T>(dst, out);
+  store8<T>(dst + 8, out + 8);
+}
+
+// im2col for the 3x3 convs after the first: x [B,H,W,C] -> a [B*Ho*Wo, 9C], pad 1.
+// One thread per (output pixel, tap, 8-channel vector): a pure 16-byte gather/scatter.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const T* __restrict__ x, T* __restrict__ a, int B, int H, int W, int C, int stride, int Ho, int Wo) {
+  constexpr int VE = 8;
+  const int vpc = C / VE;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * 9 * vpc;
+  if (idx >= total) return;
+  const int v = (int)(idx % vpc);
+  int64_t t = idx / vpc;
+  const int tap = (int)(t % 9); t /= 9;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t b = t / Ho;
+  const int yy = ho * stride - 1 + tap / 3, xx = wo * stride - 1 + tap % 3;
+  float vals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  T* dst = a + ((((b * Ho + ho) * Wo + wo) * 9 + tap) * (int64_t)C) + v * VE;
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+    const T* src = x + ((b * H + yy) * (int64_t)W + xx) * C + v * VE;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+      *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(src + 4);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    }
+  } else {
+    store8<T>(dst, vals);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, vpc = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * vpc;
+  if (idx >= total) return;
+  const int v = (int)(idx % vpc);
+  int64_t t = idx / vpc;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int64_t b = t / Ho;
+  float m[8], q[8];
+  const T* p = x + ((b * H + 2 * ho) * (int64_t)W + 2 * wo) * C + v * 8;
+  load8<T>(p, m);
+  load8<T>(p + C, q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], q[i]);
+  load8<T>(p + (int64_t)W * C, q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], q[i]);
+  load8<T>(p + (int64_t)W * C + C, q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], q[i]);
+  store8<T>(y + ((b * Ho + ho) * (int64_t)Wo + wo) * C + v * 8, m);
+}
+
+// Bilinear x2 upscale (align_corners=False; antialias is a no-op when upscaling) of an
+// NHWC image to NCHW fp32.  src coordinate = (dst + 0.5)/2 - 0.5, clamped at 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize2x_kernel(const T* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * C * Ho * Wo;
+  if (idx >= total) return;
+  const int ox = (int)(idx % Wo);
+  int64_t t = idx / Wo;
+  const int oy = (int)(t % Ho); t /= Ho;
+  const int c = (int)(t % C);
+  const int64_t b = t / C;
+  const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.0f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.0f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float fy = sy - y0, fx = sx - x0;
+  const T* xb = x + b * (int64_t)H * W * C + c;
+  const float v00 = to_f<T>(xb[((int64_t)y0 * W + x0) * C]), v01 = to_f<T>(xb[((int64_t)y0 * W + x1) * C]);
+  const float v10 = to_f<T>(xb[((int64_t)y1 * W + x0) * C]), v11 = to_f<T>(xb[((int64_t)y1 * W + x1) * C]);
+  y[idx] = (1.0f - fy) * ((1.0f - fx) * v00 + fx * v01) + fy * ((1.0f - fx) * v10 + fx * v11);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * C * H * W;
+  if (idx >= total) return;
+  const int ox = (int)(idx % W);
+  int64_t t = idx / W;
+  const int oy = (int)(t % H); t /= H;
+  const int c = (int)(t % C);
+  const int64_t b = t / C;
+  y[idx] = to_f<T>(x[((b * H + oy) * (int64_t)W + ox) * C + c]);
+}
+
+// pred_vid / max_prediction_value, batched: one warp per video.
+__global__ void __launch_bounds__(32)
+score_videos_kernel(const float* __restrict__ logits, int n_nets, int n_frames, int fpv, float* __restrict__ mean_out,
+                    int32_t* __restrict__ cls_out, float* __restrict__ val_out) {
+  const int v = blockIdx.x, lane = threadIdx.x;
+  float s0 = 0.0f, s1 = 0.0f;
+  const int rows = n_nets * fpv;
+  for (int i = lane; i < rows; i += 32) {
+    const int net = i / fpv, f = i - net * fpv;
+    const float2 l = *reinterpret_cast<const float2*>(logits + 2 * ((int64_t)net * n_frames + (int64_t)v * fpv + f));
+    s0 += 1.0f / (1.0f + expf(-l.x));
+    s1 += 1.0f / (1.0f + expf(-l.y));
+  }
+  s0 = warp_sum(s0) / (float)rows;
+  s1 = warp_sum(s1) / (float)rows;
+  if (lane == 0) {
+    mean_out[2 * v] = s0;
+    mean_out[2 * v + 1] = s1;
+    cls_out[v] = s1 > s0 ? 1 : 0;                       // torch.argmax: first maximal index on ties
+    val_out[v] = s0 > s1 ? s0 : fabsf(1.0f - s1);       // ties take the else branch (pred_func.py:128-130)
+  }
+}
+
+}  // namespace
+
+int conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b, int stride, int act, int pool,
+                  int B, int H, int W, cudaStream_t stream) {
+  GCV_REQUIRE((stride == 1 || stride == 2) && B > 0, "conv3x3_first: stride must be 1 or 2");
+  GCV_REQUIRE(!(stride == 2 && pool), "conv3x3_first: stride 2 with pooling is not a reference configuration");
+  const int Hc = (H + 2 - 3) / stride + 1, Wc = (W + 2 - 3) / stride + 1;
+  const int Ho = pool ? Hc / 2 : Hc, Wo = pool ? Wc / 2 : Wc;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    if (stride == 1 && pool)
+      conv3x3_first_kernel<T, 1, true><<<grid, 128, 0, stream>>>(x, reinterpret_cast<T*>(y), w, b, act, B, H, W, Ho, Wo);
+    else if (stride == 1)
+      conv3x3_first_kernel<T, 1, false><<<grid, 128, 0, stream>>>(x, reinterpret_cast<T*>(y), w, b, act, B, H, W, Ho, Wo);
+    else
+      conv3x3_first_kernel<T, 2, false><<<grid, 128, 0, stream>>>(x, reinterpret_cast<T*>(y), w, b, act, B, H, W, Ho, Wo);
+    return check_launch("conv3x3_first");
+  });
+}
+
+int im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, cudaStream_t stream) {
+  GCV_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2), "im2col3x3: C must be a multiple of 8 (C=%d)", C);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * 9 * (C / 8);
+  GCV_REQUIRE((total + 255) / 256 < 2147483647LL, "im2col3x3: too large");
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    im2col3x3_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(a), B, H, W, C, stride, Ho, Wo);
+    return check_launch("im2col3x3");
+  });
+}
+
+int maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t stream) {
+  GCV_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "maxpool2: C must be a multiple of 8");
+  const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    maxpool2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const T*>(x),
+                                                                             reinterpret_cast<T*>(y), B, H, W, C);
+    return check_launch("maxpool2");
+  });
+}
+
+int resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+  const int64_t total = (int64_t)B * C * 4 * H * W;
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    resize2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const T*>(x), y, B, H, W, C);
+    return check_launch("resize2x_to_nchw");
+  });
+}
+
+int nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream) {
+  const int64_t total = (int64_t)B * C * H * W;
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    nhwc_to_nchw_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const T*>(x), y, B, H, W, C);
+    return check_launch("nhwc_to_nchw_f32");
+  });
+}
+
+int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* mean_out, int32_t* cls_out,
+                 float* val_out, cudaStream_t stream) {
+  GCV_REQUIRE(n_nets > 0 && fpv > 0 && n_frames >= fpv && n_frames % fpv == 0,
+              "score_videos: n_frames (%d) must be a positive multiple of frames_per_video (%d)", n_frames, fpv);
+  score_videos_kernel<<<n_frames / fpv, 32, 0, stream>>>(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out);
+  return check_launch("score_videos");
+}
+
+}  // namespace gcv

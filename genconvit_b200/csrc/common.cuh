@@ -1,0 +1,127 @@
+// Shared device/host helpers for the genconvit_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/genconvit_b200.h"
+
+namespace gcv {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define GCV_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      gcv::set_error(__VA_ARGS__);             \
+      return GCV_ERR_BAD_ARG;                  \
+    }                                          \
+  } while (0)
+
+// ---- element conversion -----------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// pack two floats into one 32-bit word of T pairs (16-bit types only)
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<__half2*>(&w));
+}
+
+// load / store 8 consecutive elements (16-byte aligned for 16-bit T, 32-byte for float)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float* v) {
+  if constexpr (sizeof(T) == 4) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    float2 f;
+    f = unpack2<T>(q.x); v[0] = f.x; v[1] = f.y;
+    f = unpack2<T>(q.y); v[2] = f.x; v[3] = f.y;
+    f = unpack2<T>(q.z); v[4] = f.x; v[5] = f.y;
+    f = unpack2<T>(q.w); v[6] = f.x; v[7] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float* v) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 q;
+    q.x = pack2<T>(v[0], v[1]); q.y = pack2<T>(v[2], v[3]);
+    q.z = pack2<T>(v[4], v[5]); q.w = pack2<T>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- activations ---------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GCV_ACT_GELU: return gelu_erf(v);
+    case GCV_ACT_RELU: return fmaxf(v, 0.0f);
+    case GCV_ACT_LEAKY: return v > 0.0f ? v : 0.01f * v;
+    default: return v;
+  }
+}
+
+// ---- GEMM epilogue (shared by the tcgen05 and the SIMT back ends) -----------------
+// One output element; see gcv_epilogue in the public header for the order of operations.
+template <typename T>
+__device__ __forceinline__ void epilogue_one(const gcv_epilogue& ep, int64_t m, int n, int N, float acc, void* D) {
+  float v = acc + (ep.bias ? __ldg(ep.bias + n) : 0.0f);
+  v = apply_act(v, ep.act);
+  if (ep.eps) {
+    const float mu = v;
+    const int hw = n / ep.eps_c, c = n - hw * ep.eps_c;
+    const float e = __ldg(ep.eps + m * (int64_t)N + (int64_t)c * ep.eps_hw + hw);
+    if (ep.mu_out) ep.mu_out[m * (int64_t)N + n] = mu;
+    v = e * expf(0.5f * mu) + mu;
+  }
+  if (ep.gamma) v *= __ldg(ep.gamma + n);
+  if (ep.residual) v += to_f<T>(reinterpret_cast<const T*>(ep.residual)[m * ep.ldr + n]);
+  int64_t off;
+  if (ep.store == GCV_STORE_PIXEL_SHUFFLE2) {
+    const int ij = n / ep.ps_co, co = n - ij * ep.ps_co;
+    const int64_t hw = (int64_t)ep.ps_h * ep.ps_w;
+    const int64_t b = m / hw;
+    const int r = (int)(m - b * hw);
+    const int h = r / ep.ps_w, w = r - h * ep.ps_w;
+    off = ((b * (2 * ep.ps_h) + 2 * h + (ij >> 1)) * (int64_t)(2 * ep.ps_w) + 2 * w + (ij & 1)) * ep.ps_co + co;
+  } else {
+    off = m * ep.ldd + n;
+  }
+  if (ep.out_f32) reinterpret_cast<float*>(D)[off] = v;
+  else reinterpret_cast<T*>(D)[off] = from_f<T>(v);
+}
+
+}  // namespace gcv

@@ -1,0 +1,359 @@
+// Memory-bound ConvNeXt kernels (NHWC): depthwise 7x7 + LayerNorm, LayerNorm2d +
+// 2x2 patchify, stem patchify, row LayerNorm, global-average-pool + LayerNorm.
+// timm==0.6.5 ConvNeXt as reached from reference model/genconvit_ed.py:68,
+// model/genconvit_vae.py:97 (arithmetic restated in oracle/backbones.py).
+#include "common.cuh"
+
+namespace gcv {
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// Depthwise 7x7 (pad 3) + bias + LayerNorm over C.
+// CTA = 4 x 8 output pixels, all C channels, 128 threads.  Channels are processed in
+// chunks of 64: the (4+6) x (8+6) input halo of the chunk is staged in shared
+// memory; thread (row r, channel pair p) keeps 8 pixels x 2 channels of fp32
+// accumulators and slides along the row so every staged value feeds 7 taps.  The
+// conv outputs of the tile are parked in shared memory ([32][C] fp32) and a second
+// phase normalises one pixel per warp with shuffle reductions and writes coalesced.
+// ---------------------------------------------------------------------------------
+constexpr int DW_TH = 4, DW_TW = 8, DW_CK = 64;
+constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+dwconv7_ln_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ taps,
+                  const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                  float eps, int H, int W, int C, int tiles_w, int tiles_h) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  T* halo = reinterpret_cast<T*>(smem);                                     // [DW_HH][DW_HW][DW_CK]
+  float* outs = reinterpret_cast<float*>(smem + DW_HH * DW_HW * DW_CK * sizeof(T));  // [32][C]
+
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; t /= tiles_h;
+  const int b = t;
+  const int h0 = th * DW_TH, w0 = tw * DW_TW;
+  const T* xb = x + (int64_t)b * H * W * C;
+
+  const int r = threadIdx.x >> 5;          // output row within the tile
+  const int pr = threadIdx.x & 31;         // channel pair within the chunk
+
+  for (int c0 = 0; c0 < C; c0 += DW_CK) {
+    const int cw = min(DW_CK, C - c0);     // channels in this chunk (multiple of 32)
+    // ---- stage the halo: 16-byte vectors, zero outside the image ----
+    constexpr int VE = 16 / sizeof(T);
+    const int vec_per_px = cw / VE;
+    for (int i = threadIdx.x; i < DW_HH * DW_HW * vec_per_px; i += blockDim.x) {
+      const int v = i % vec_per_px, px = i / vec_per_px;
+      const int hy = px / DW_HW, hx = px - hy * DW_HW;
+      const int gy = h0 + hy - 3, gx = w0 + hx - 3;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        val = *reinterpret_cast<const uint4*>(xb + ((int64_t)gy * W + gx) * C + c0 + v * VE);
+      *reinterpret_cast<uint4*>(halo + px * DW_CK + v * VE) = val;
+    }
+    __syncthreads();
+    if (2 * pr < cw) {
+      const int c = c0 + 2 * pr;
+      float acc0[DW_TW], acc1[DW_TW];
+      const float b0 = bias[c], b1 = bias[c + 1];
+#pragma unroll
+      for (int i = 0; i < DW_TW; ++i) { acc0[i] = b0; acc1[i] = b1; }
+#pragma unroll 1
+      for (int dy = 0; dy < 7; ++dy) {
+        float w0r[7], w1r[7];
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+          const float2 wv = __ldg(reinterpret_cast<const float2*>(taps + (dy * 7 + dx) * C + c));
+          w0r[dx] = wv.x; w1r[dx] = wv.y;
+        }
+        const T* row = halo + ((r + dy) * DW_HW) * DW_CK + 2 * pr;
+#pragma unroll
+        for (int ix = 0; ix < DW_HW; ++ix) {
+          float v0, v1;
+          if constexpr (sizeof(T) == 4) {
+            const float2 f = *reinterpret_cast<const float2*>(row + ix * DW_CK);
+            v0 = f.x; v1 = f.y;
+          } else {
+            const float2 f = unpack2<T>(*reinterpret_cast<const uint32_t*>(row + ix * DW_CK));
+            v0 = f.x; v1 = f.y;
+          }
+#pragma unroll
+          for (int dx = 0; dx < 7; ++dx) {
+            const int ox = ix - dx;
+            if (ox >= 0 && ox < DW_TW) {
+              acc0[ox] = fmaf(v0, w0r[dx], acc0[ox]);
+              acc1[ox] = fmaf(v1, w1r[dx], acc1[ox]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < DW_TW; ++i)
+        *reinterpret_cast<float2*>(outs + (r * DW_TW + i) * C + c) = make_float2(acc0[i], acc1[i]);
+    }
+    __syncthreads();
+  }
+
+  // ---- LayerNorm: warp w normalises the 8 pixels of tile row w ----
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gy = h0 + warp;
+  if (gy >= H) return;
+  const float inv_c = 1.0f / (float)C;
+  for (int i = 0; i < DW_TW; ++i) {
+    const int gx = w0 + i;
+    if (gx >= W) break;
+    const float* o = outs + (warp * DW_TW + i) * C;
+    float s = 0.0f;
+    for (int c = 2 * lane; c < C; c += 64) { const float2 f = *reinterpret_cast<const float2*>(o + c); s += f.x + f.y; }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.0f;
+    for (int c = 2 * lane; c < C; c += 64) {
+      const float2 f = *reinterpret_cast<const float2*>(o + c);
+      q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+    T* dst = y + (((int64_t)b * H + gy) * W + gx) * C;
+    for (int c = 2 * lane; c < C; c += 64) {
+      const float2 f = *reinterpret_cast<const float2*>(o + c);
+      const float2 g = __ldg(reinterpret_cast<const float2*>(ln_w + c));
+      const float2 be = __ldg(reinterpret_cast<const float2*>(ln_b + c));
+      const float a0 = (f.x - mean) * rstd * g.x + be.x, a1 = (f.y - mean) * rstd * g.y + be.y;
+      if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dst + c) = make_float2(a0, a1);
+      else *reinterpret_cast<uint32_t*>(dst + c) = pack2<T>(a0, a1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Per-row LayerNorm helpers: one warp per row, row cached in registers (C <= 32*MAXV).
+// ---------------------------------------------------------------------------------
+constexpr int LN_MAXV = 48;   // up to C = 1536
+
+template <typename T>
+__device__ __forceinline__ void warp_ln_row(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ w,
+                                            const float* __restrict__ b, float eps, int C, int lane) {
+  float v[LN_MAXV];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < C ? to_f<T>(src[c]) : 0.0f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) q += (v[i] - mean) * (v[i] - mean);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) dst[c] = from_f<T>((v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
+                      const float* __restrict__ b, float eps, int64_t rows, int C) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  warp_ln_row<T>(x + row * C, y + row * C, w, b, eps, C, threadIdx.x & 31);
+}
+
+// LayerNorm2d over C of every pixel, written straight into the im2col matrix of the
+// following 2x2 stride-2 conv: pixel (2ho+kh, 2wo+kw) -> row (b,ho,wo), columns
+// [(kh*2+kw)*C, +C).  Pixels of an odd last row/column are dropped (floor semantics).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_patchify2_kernel(const T* __restrict__ x, T* __restrict__ a, const float* __restrict__ w,
+                    const float* __restrict__ b, float eps, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t idx = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)B * Ho * 2 * Wo * 2;
+  if (idx >= total) return;
+  const int wi = (int)(idx % (2 * Wo));
+  const int64_t t = idx / (2 * Wo);
+  const int hi = (int)(t % (2 * Ho));
+  const int64_t bi = t / (2 * Ho);
+  const T* src = x + ((bi * H + hi) * W + wi) * C;
+  const int64_t row = (bi * Ho + (hi >> 1)) * Wo + (wi >> 1);
+  T* dst = a + row * (4 * (int64_t)C) + ((hi & 1) * 2 + (wi & 1)) * C;
+  warp_ln_row<T>(src, dst, w, b, eps, C, threadIdx.x & 31);
+}
+
+// Stem im2col (4x4 stride 4, 3 channels): row (b,ho,wo), column (kh*4+kw)*3 + c.
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_patchify_nchw_kernel(const float* __restrict__ x, T* __restrict__ a, int B, int H, int W) {
+  const int Ho = H / 4, Wo = W / 4;
+  // one thread per (b, ho, kh, wo): reads 3 x float4 (coalesced along wo), writes 12 contiguous elements
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * 4 * Wo;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo);
+  int64_t t = idx / Wo;
+  const int kh = (int)(t & 3); t >>= 2;
+  const int ho = (int)(t % Ho);
+  const int64_t b = t / Ho;
+  float4 px[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    px[c] = *reinterpret_cast<const float4*>(x + ((b * 3 + c) * H + (ho * 4 + kh)) * (int64_t)W + wo * 4);
+  T* dst = a + ((b * Ho + ho) * Wo + wo) * 48 + kh * 12;
+  const float v[12] = {px[0].x, px[1].x, px[2].x, px[0].y, px[1].y, px[2].y,
+                       px[0].z, px[1].z, px[2].z, px[0].w, px[1].w, px[2].w};
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dst[i] = from_f<T>(v[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_patchify_nhwc_kernel(const T* __restrict__ x, T* __restrict__ a, int B, int H, int W) {
+  const int Ho = H / 4, Wo = W / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * 4 * Wo;
+  if (idx >= total) return;
+  const int wo = (int)(idx % Wo);
+  int64_t t = idx / Wo;
+  const int kh = (int)(t & 3); t >>= 2;
+  const int ho = (int)(t % Ho);
+  const int64_t b = t / Ho;
+  const T* src = x + ((b * H + ho * 4 + kh) * (int64_t)W + wo * 4) * 3;
+  T* dst = a + ((b * Ho + ho) * Wo + wo) * 48 + kh * 12;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dst[i] = src[i];
+}
+
+// Global average pool over HW then LayerNorm over C: one CTA per image, thread per channel (strided).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_ln_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ w, const float* __restrict__ b,
+               float eps, int HW, int C) {
+  __shared__ float red[8];
+  __shared__ float stat;
+  const T* xb = x + (int64_t)blockIdx.x * HW * C;
+  constexpr int MAXV = 8;  // C <= 2048
+  float v[MAXV];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    float acc = 0.0f;
+    if (c < C) {
+      for (int p = 0; p < HW; ++p) acc += to_f<T>(xb[(int64_t)p * C + c]);
+      acc /= (float)HW;
+    }
+    v[i] = acc;
+    s += acc;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float tsum = 0; for (int i = 0; i < 8; ++i) tsum += red[i]; stat = tsum / (float)C; }
+  __syncthreads();
+  const float mean = stat;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { const int c = threadIdx.x + i * 256; if (c < C) q += (v[i] - mean) * (v[i] - mean); }
+  q = warp_sum(q);
+  __syncthreads();
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) { float tsum = 0; for (int i = 0; i < 8; ++i) tsum += red[i]; stat = rsqrtf(tsum / (float)C + eps); }
+  __syncthreads();
+  const float rstd = stat;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < C) y[(int64_t)blockIdx.x * C + c] = from_f<T>((v[i] - mean) * rstd * w[c] + b[c]);
+  }
+}
+
+template <typename F>
+int dispatch(int dtype, F&& f) {
+  switch (dtype) {
+    case GCV_F32: return f(float{});
+    case GCV_BF16: return f(__nv_bfloat16{});
+    case GCV_F16: return f(__half{});
+    default: set_error("bad dtype %d", dtype); return GCV_ERR_BAD_ARG;
+  }
+}
+
+}  // namespace
+
+int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
+               const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream) {
+  GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
+  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
+  const int64_t grid = (int64_t)B * tiles_w * tiles_h;
+  GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    const size_t smem = DW_HH * DW_HW * DW_CK * sizeof(T) + (size_t)DW_TH * DW_TW * C * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(dwconv7_ln_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
+    }
+    GCV_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C=%d needs %zu B of shared memory", C, smem);
+    dwconv7_ln_kernel<T><<<(unsigned)grid, 128, smem, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y),
+                                                               taps, bias, ln_w, ln_b, eps, H, W, C, tiles_w, tiles_h);
+    return check_launch("dwconv7_ln");
+  });
+}
+
+int ln_patchify2(int dtype, const void* x, void* a, const float* w, const float* b, float eps, int B, int H, int W, int C,
+                 cudaStream_t stream) {
+  GCV_REQUIRE(C <= 32 * LN_MAXV && H >= 2 && W >= 2, "ln_patchify2: unsupported C=%d H=%d W=%d", C, H, W);
+  const int64_t total = (int64_t)B * (H / 2) * 2 * (W / 2) * 2;
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    ln_patchify2_kernel<T><<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(
+        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(a), w, b, eps, B, H, W, C);
+    return check_launch("ln_patchify2");
+  });
+}
+
+int stem_patchify(int dtype, bool nchw, const void* x, void* a, int B, int H, int W, cudaStream_t stream) {
+  GCV_REQUIRE(H % 4 == 0 && W % 4 == 0, "stem_patchify: H, W must be multiples of 4");
+  const int64_t total = (int64_t)B * (H / 4) * 4 * (W / 4);
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (nchw)
+      stem_patchify_nchw_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<T*>(a), B, H, W);
+    else
+      stem_patchify_nhwc_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(a), B, H, W);
+    return check_launch("stem_patchify");
+  });
+}
+
+int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
+                   cudaStream_t stream) {
+  GCV_REQUIRE(C <= 32 * LN_MAXV && rows > 0, "layernorm_rows: unsupported C=%d", C);
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    layernorm_rows_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
+        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, b, eps, rows, C);
+    return check_launch("layernorm_rows");
+  });
+}
+
+int pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int B, int HW, int C,
+            cudaStream_t stream) {
+  GCV_REQUIRE(C <= 2048 && B > 0 && HW > 0, "pool_ln: unsupported C=%d", C);
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    pool_ln_kernel<T><<<B, 256, 0, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, b, eps, HW, C);
+    return check_launch("pool_ln");
+  });
+}
+
+}  // namespace gcv

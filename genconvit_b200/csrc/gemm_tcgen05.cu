@@ -1,0 +1,430 @@
+// TMA-fed tcgen05 GEMM with TMEM accumulators for sm_100a.
+//
+//   D[M,N] = epilogue(A[M,K] * B[N,K]^T)      A, B: bf16 or fp16, K-major; fp32 accumulate
+//
+// Replaces every nn.Linear / patchify-conv / im2col'd conv / k2s2 transposed conv
+// contraction of the GenConViT forward (see include/genconvit_b200.h, gcv_gemm).
+//
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and
+//               B (block_n x 64) K-slices into a ring of 128B-swizzled smem stages
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=block_n, K=16)
+//               into one of two TMEM accumulator stages; tcgen05.commit frees smem
+//               stages and publishes finished accumulators
+//   warps 2..9  epilogue: tcgen05.ld of the fp32 accumulator (thread = row, 32
+//               columns per load), fused bias / activation / layer-scale+residual /
+//               VAE reparameterisation, 16-byte stores (rows or convT pixel shuffle)
+// The two TMEM stages let tile i's epilogue overlap tile i+1's MMAs.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gcv {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kMaxStages = 8;
+constexpr int kTileSmem = 192 * 1024;
+constexpr int kCtrlSmem = 1024;
+constexpr int kDynSmem = kCtrlSmem + 1024 + kTileSmem;   // +1024 alignment slack
+constexpr uint32_t kTmemCols = 512;
+
+struct Params {
+  int64_t M;
+  int N, K;
+  int block_n, num_stages;
+  int tiles_m, tiles_n;
+  uint32_t idesc;
+  int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
+  gcv_epilogue ep;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();      // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows are 128 B, 8-row atoms are 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), SWIZZLE_128B=2 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                  // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+
+// ---- vectorised epilogue: 8 consecutive columns of one row ---------------------
+template <typename T>
+__device__ __forceinline__ void epilogue_vec8(const gcv_epilogue& ep, int64_t m, int n, float* v, void* D) {
+  if (ep.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (ep.act != GCV_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+  }
+  if (ep.gamma) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+  }
+  if (ep.residual) {
+    float r[8];
+    load8<T>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + n, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += r[j];
+  }
+  int64_t off;
+  if (ep.store == GCV_STORE_PIXEL_SHUFFLE2) {
+    const int ij = n / ep.ps_co, co = n - ij * ep.ps_co;
+    const int64_t hw = (int64_t)ep.ps_h * ep.ps_w;
+    const int64_t b = m / hw;
+    const int r = (int)(m - b * hw);
+    const int h = r / ep.ps_w, w = r - h * ep.ps_w;
+    off = ((b * (2 * ep.ps_h) + 2 * h + (ij >> 1)) * (int64_t)(2 * ep.ps_w) + 2 * w + (ij & 1)) * ep.ps_co + co;
+  } else {
+    off = m * ep.ldd + n;
+  }
+  if (ep.out_f32) store8<float>(reinterpret_cast<float*>(D) + off, v);
+  else store8<T>(reinterpret_cast<T*>(D) + off, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    void* D, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // control block: barriers + TMEM base pointer
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.block_n * BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(tmem_full + s), 1);
+      mbar_init(smem_u32(tmem_empty + s), kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+          const uint32_t fb = smem_u32(full_bar + stage);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = tiles_base + stage * stage_bytes;
+          tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
+          tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(smem_u32(tmem_empty + as), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(full_bar + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = tiles_base + stage * stage_bytes;
+          const int k_left = p.K - kb * BK;
+          const int kmma = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
+          for (int k = 0; k < kmma; ++k) {
+            const uint64_t ad = umma_desc(sa + k * 32);
+            const uint64_t bd = umma_desc(sa + a_bytes + k * 32);
+            tc_mma(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(empty_bar + stage));       // frees the smem stage once these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(tmem_full + as));             // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                            // the two warps of a quarter split the column chunks
+    const int chunks = p.block_n / 32;
+    const bool vec_ok = p.vec_ok != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int as = it & 1;
+      mbar_wait(smem_u32(tmem_full + as), (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_blk * BM + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
+      for (int c = half; c < chunks; c += 2) {
+        uint32_t r[32];
+        tc_ld32(t_row + c * 32, r);
+        tc_wait_ld();
+        const int n0 = n_blk * p.block_n + c * 32;
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + j * 8;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
+            if (vec_ok && n + 8 <= p.N) {
+              epilogue_vec8<T>(p.ep, m, n, v, D);
+            } else {
+              for (int e = 0; e < 8; ++e)
+                if (n + e < p.N) epilogue_one<T>(p.ep, m, n + e, p.N, v[e], D);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not resolvable (no CUDA driver?)");
+    return GCV_ERR_NO_DRIVER;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == GCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld k=%lld ld=%lld box_rows=%d)", (int)r,
+              (long long)rows, (long long)k, (long long)ld, box_rows);
+    return GCV_ERR_CUDA;
+  }
+  return GCV_OK;
+}
+
+int pick_block_n(int64_t M, int N, int sms) {
+  // Largest tile that still gives every SM work; N tiles must be multiples of 32 (epilogue chunk) <= 256.
+  const int cands[] = {256, 192, 128, 96, 64, 32};
+  const int64_t tiles_m = (M + BM - 1) / BM;
+  int best = 32;
+  for (int c : cands) {
+    if (c > ((N + 31) / 32) * 32) continue;          // tile wider than the problem
+    const int tn = (N + c - 1) / c;
+    const int waste = tn * c - N;
+    if (waste * 8 > N && c > 32) continue;           // >12.5% padded columns
+    best = c;
+    if (tiles_m * tn >= sms) break;                  // big enough to fill the machine
+  }
+  return best;
+}
+
+}  // namespace
+
+bool tcgen05_eligible(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t K) {
+  if (dtype != GCV_BF16 && dtype != GCV_F16) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if (lda % 8 || ldb % 8 || K % 8 || K < 8) return false;
+  return true;
+}
+
+int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M, int64_t N,
+                 int64_t K, const gcv_epilogue* ep, int force_block_n, cudaStream_t stream) {
+  GCV_REQUIRE(tcgen05_eligible(dtype, A, lda, B, ldb, K),
+              "tcgen05 GEMM needs bf16/fp16, 16-byte aligned A/B and K, lda, ldb multiples of 8 (K=%lld lda=%lld ldb=%lld)",
+              (long long)K, (long long)lda, (long long)ldb);
+  GCV_REQUIRE(M > 0 && N > 0 && N < (1 << 30), "bad GEMM shape");
+  static int sms = 0;
+  static bool attr_set[2] = {false, false};
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  Params p{};
+  p.M = M; p.N = (int)N; p.K = (int)K;
+  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, (int)N, sms);
+  GCV_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "block_n must be a multiple of 32 in [32,256]");
+  const int stage_bytes = BM * BK * 2 + p.block_n * BK * 2;
+  p.num_stages = kTileSmem / stage_bytes;
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  p.tiles_m = (int)((M + BM - 1) / BM);
+  p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
+  const uint32_t fmt = dtype == GCV_BF16 ? 1u : 0u;
+  // cute::UMMA::InstrDescriptor: c_format F32 [4,6), a/b format [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  p.ep = *ep;
+  {
+    const size_t es = ep->out_f32 ? 4 : 2;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool ok = ep->eps == nullptr && al16(D) && (!ep->bias || al16(ep->bias)) && (!ep->gamma || al16(ep->gamma));
+    if (ep->store == GCV_STORE_ROWS) ok = ok && (ep->ldd * es) % 16 == 0;
+    else ok = ok && ep->ps_co % 8 == 0;
+    if (ep->residual) ok = ok && al16(ep->residual) && ep->ldr % 8 == 0;
+    p.vec_ok = ok ? 1 : 0;
+  }
+
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dtype, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&mb, dtype, B, N, K, ldb, p.block_n);
+  if (rc) return rc;
+
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const int ti = dtype == GCV_BF16 ? 0 : 1;
+  if (!attr_set[ti]) {
+    cudaError_t e = dtype == GCV_BF16
+                        ? cudaFuncSetAttribute(gemm_tcgen05_kernel<__nv_bfloat16>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)
+                        : cudaFuncSetAttribute(gemm_tcgen05_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               kDynSmem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", kDynSmem, cudaGetErrorString(e));
+      return GCV_ERR_CUDA;
+    }
+    attr_set[ti] = true;
+  }
+  if (dtype == GCV_BF16)
+    gemm_tcgen05_kernel<__nv_bfloat16><<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
+  else
+    gemm_tcgen05_kernel<__half><<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
+  return check_launch("gemm_tcgen05");
+}
+
+}  // namespace gcv

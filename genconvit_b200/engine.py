@@ -1,0 +1,335 @@
+"""Host-side forward of GenConViT on the sm_100a kernel library.
+
+Everything here is orchestration: weights are re-packed once into kernel layouts
+(NHWC / K-major, BatchNorm folded, the VAE ``mu`` matrix permuted from the
+reference's NCHW-flatten order to NHWC), and a forward is a fixed sequence of
+C-ABI kernel launches on the current torch stream (capturable in a CUDA graph).
+torch supplies device memory and the stream only; no torch operator touches an
+activation.
+
+Reference call sites are cited per function; the arithmetic contract is the
+CPU oracle (``oracle/``), which is never imported from here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as L
+
+DEPTHS = (3, 3, 9, 3)
+DIMS = (96, 192, 384, 768)
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _cd(t, dev, dt):
+    return t.detach().to(device=dev, dtype=torch.float32).to(dt).contiguous()
+
+
+def _empty(shape, dt, dev):
+    return torch.empty(shape, dtype=dt, device=dev)
+
+
+class PackedConvNeXt:
+    """Kernel-layout copy of a timm-style ConvNeXt-T ``state_dict`` (prefix-free keys)."""
+
+    def __init__(self, sd, dev, dt):
+        self.dev, self.dt = dev, dt
+        w = sd["stem.0.weight"]                                   # [96,3,4,4] -> [96, (kh,kw,c)]
+        self.stem_w = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], 48), dev, dt)
+        self.stem_b = _f32(sd["stem.0.bias"], dev)
+        self.stem_ln = (_f32(sd["stem.1.weight"], dev), _f32(sd["stem.1.bias"], dev))
+        self.stages = []
+        for s, depth in enumerate(DEPTHS):
+            st = {"blocks": []}
+            p = f"stages.{s}."
+            if s > 0:
+                st["ds_ln"] = (_f32(sd[p + "downsample.0.weight"], dev), _f32(sd[p + "downsample.0.bias"], dev))
+                w = sd[p + "downsample.1.weight"]                 # [Co,Ci,2,2] -> [Co, (kh,kw,ci)]
+                st["ds_w"] = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), dev, dt)
+                st["ds_b"] = _f32(sd[p + "downsample.1.bias"], dev)
+            for k in range(depth):
+                q = f"{p}blocks.{k}."
+                c = DIMS[s]
+                st["blocks"].append(dict(
+                    taps=_f32(sd[q + "conv_dw.weight"].reshape(c, 49).t(), dev),     # [49, C]
+                    dw_b=_f32(sd[q + "conv_dw.bias"], dev),
+                    ln_w=_f32(sd[q + "norm.weight"], dev), ln_b=_f32(sd[q + "norm.bias"], dev),
+                    fc1_w=_cd(sd[q + "mlp.fc1.weight"], dev, dt), fc1_b=_f32(sd[q + "mlp.fc1.bias"], dev),
+                    fc2_w=_cd(sd[q + "mlp.fc2.weight"], dev, dt), fc2_b=_f32(sd[q + "mlp.fc2.bias"], dev),
+                    gamma=_f32(sd[q + "gamma"], dev)))
+            self.stages.append(st)
+        self.head_ln = (_f32(sd["head.norm.weight"], dev), _f32(sd["head.norm.bias"], dev))
+        self.head_w = _cd(sd["head.fc.weight"], dev, dt)
+        self.head_b = _f32(sd["head.fc.bias"], dev)
+
+    def forward_tokens(self, a0, segments, outs, act, backend=L.GEMM_AUTO):
+        """Run stem-GEMM .. head on pre-patchified tokens.
+
+        a0       [sum_i B_i*H_i*W_i, 48] stem im2col rows, segment after segment
+        segments list of (B, H, W) *after* the 4x4 stem (e.g. (N, 56, 56)); segments share the
+                 weights, so all GEMMs run once over the concatenated tokens
+        outs     list of (first_image, n_images, view, ldd): head logits of images
+                 [first, first+n) are written to ``view`` (a [n, >=1000]-column window with
+                 leading dimension ldd) with ``act`` already applied -- the reference applies
+                 its GELU/ReLU to the concatenated backbone logits before ``fc``
+        timm ConvNeXt.forward = head(stages(stem(x))) as reached from reference
+        genconvit_ed.py:82-83 / genconvit_vae.py:111-112.
+        """
+        dev, dt = self.dev, self.dt
+        m = a0.shape[0]
+        x = _empty((m, DIMS[0]), dt, dev)
+        L.gemm(a0, self.stem_w, x, m, DIMS[0], 48, bias=self.stem_b, backend=backend)
+        L.layernorm_rows(x, x, self.stem_ln[0], self.stem_ln[1], 1e-6, m, DIMS[0])
+        segs = list(segments)
+        for s, st in enumerate(self.stages):
+            c = DIMS[s]
+            if s > 0:
+                cin = DIMS[s - 1]
+                new = [(b, h // 2, w // 2) for b, h, w in segs]
+                m2 = sum(b * h * w for b, h, w in new)
+                a = _empty((m2, 4 * cin), dt, dev)
+                ro = ri = 0
+                for (b, h, w), (_, h2, w2) in zip(segs, new):
+                    L.ln_patchify2(x[ri:], a[ro:], st["ds_ln"][0], st["ds_ln"][1], 1e-6, b, h, w, cin)
+                    ri += b * h * w
+                    ro += b * h2 * w2
+                x = _empty((m2, c), dt, dev)
+                L.gemm(a, st["ds_w"], x, m2, c, 4 * cin, bias=st["ds_b"], backend=backend)
+                segs, m = new, m2
+            y = _empty((m, c), dt, dev)
+            hid = _empty((m, 4 * c), dt, dev)
+            for blk in st["blocks"]:
+                r = 0
+                for b, h, w in segs:
+                    L.dwconv7_ln(x[r:], y[r:], blk["taps"], blk["dw_b"], blk["ln_w"], blk["ln_b"], 1e-6, b, h, w, c)
+                    r += b * h * w
+                L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
+                L.gemm(hid, blk["fc2_w"], x, m, c, 4 * c, bias=blk["fc2_b"], gamma=blk["gamma"], residual=x, ldr=c,
+                       backend=backend)
+        c = DIMS[3]
+        n_img = sum(b for b, _, _ in segs)
+        pooled = _empty((n_img, c), dt, dev)
+        r = i = 0
+        for b, h, w in segs:
+            L.pool_ln(x[r:], pooled[i:], self.head_ln[0], self.head_ln[1], 1e-6, b, h * w, c)
+            r += b * h * w
+            i += b
+        for first, cnt, view, ldd in outs:
+            L.gemm(pooled[first:], self.head_w, view, cnt, 1000, c, bias=self.head_b, act=act, ldd=ldd,
+                   out_f32=view.dtype == torch.float32 and dt != torch.float32, backend=backend)
+
+    def forward_images(self, x, act=L.ACT_NONE, backend=L.GEMM_AUTO):
+        """``backbone(x)`` for fp32 NCHW frames -> fp32 [N,1000] ImageNet logits."""
+        n, _, hh, ww = x.shape
+        a0 = _empty((n * (hh // 4) * (ww // 4), 48), self.dt, self.dev)
+        L.stem_patchify_nchw(x, a0, n, hh, ww)
+        out = _empty((n, 1000), torch.float32, self.dev)
+        self.forward_tokens(a0, [(n, hh // 4, ww // 4)], [(0, n, out, 1000)], act, backend)
+        return out
+
+
+def _pack_conv3x3(w, dev, dt):
+    """[Co,Ci,3,3] -> [Co, (kh,kw,ci)] matching gcv_im2col3x3's column order."""
+    return _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), dev, dt)
+
+
+def _pack_convt(w, b, dev, dt):
+    """ConvTranspose2d k2 s2 weight [Ci,Co,2,2] -> GEMM B [(i,j,co), Ci] and the bias repeated per tap."""
+    co = w.shape[1]
+    return _cd(w.permute(2, 3, 1, 0).reshape(4 * co, w.shape[0]), dev, dt), _f32(b.repeat(4), dev)
+
+
+def _run_convt_stack(x, layers, b, h, w, act, dt, dev, backend):
+    """x: [B*h*w, Ci] tokens -> NHWC image after the k2s2 transposed-conv stack (pixel-shuffle epilogue)."""
+    for wt, bias in layers:
+        co, ci = wt.shape[0] // 4, wt.shape[1]
+        out = _empty((b * 4 * h * w, co), dt, dev)
+        L.gemm(x, wt, out, b * h * w, 4 * co, ci, bias=bias, act=act, store=L.STORE_PIXEL_SHUFFLE2, ps=(h, w, co),
+               backend=backend)
+        x, h, w = out, 2 * h, 2 * w
+    return x, h, w
+
+
+def _heads(cat, n, fc_w, fc_b, fc2_w, fc2_b, act, dt, dev, backend):
+    """fc2(act(fc(cat))) -- ``cat`` already holds act(concatenated backbone logits).  -> fp32 [n,2]."""
+    hid = _empty((n, 512), dt, dev)          # 500 columns used; leading dimension padded for 16-byte rows
+    L.gemm(cat, fc_w, hid, n, 500, 2000, bias=fc_b, act=act, ldd=512, backend=backend)
+    logits = _empty((n, 2), torch.float32, dev)
+    L.gemm(hid, fc2_w, logits, n, 2, 500, lda=512, bias=fc2_b, out_f32=dt != torch.float32, backend=backend)
+    return logits
+
+
+class PackedED:
+    """Network A (reference model/genconvit_ed.py:63-89)."""
+
+    def __init__(self, sd, dev, dt):
+        self.dev, self.dt = dev, dt
+        self.enc0_w = _f32(sd["encoder.features.0.weight"], dev)          # direct fp32 conv, OIHW
+        self.enc0_b = _f32(sd["encoder.features.0.bias"], dev)
+        self.enc = [(_pack_conv3x3(sd[f"encoder.features.{i}.weight"], dev, dt), _f32(sd[f"encoder.features.{i}.bias"], dev))
+                    for i in (3, 6, 9, 12)]
+        self.dec = [_pack_convt(sd[f"decoder.features.{i}.weight"], sd[f"decoder.features.{i}.bias"], dev, dt)
+                    for i in (0, 2, 4, 6, 8)]
+        self.backbone = PackedConvNeXt({k[len("backbone."):]: v for k, v in sd.items()
+                                        if k.startswith("backbone.") and not k.startswith("backbone.patch_embed.")}, dev, dt)
+        self.fc_w, self.fc_b = _cd(sd["fc.weight"], dev, dt), _f32(sd["fc.bias"], dev)
+        self.fc2_w, self.fc2_b = _cd(sd["fc2.weight"], dev, dt), _f32(sd["fc2.bias"], dev)
+
+    def encode(self, x, backend=L.GEMM_AUTO):
+        """Encoder (genconvit_ed.py:13-36): -> ([N*49, 256] tokens, 7, 7)."""
+        dev, dt = self.dev, self.dt
+        n, _, hh, ww = x.shape
+        h, w, c = hh // 2, ww // 2, 16
+        e = _empty((n * h * w, c), dt, dev)
+        L.conv3x3_first(x, e, self.enc0_w, self.enc0_b, 1, L.ACT_RELU, True, n, hh, ww)
+        for wt, bias in self.enc:
+            co = wt.shape[0]
+            a = _empty((n * h * w, 9 * c), dt, dev)
+            L.im2col3x3(e, a, n, h, w, c, 1)
+            full = _empty((n * h * w, co), dt, dev)
+            L.gemm(a, wt, full, n * h * w, co, 9 * c, bias=bias, act=L.ACT_RELU, backend=backend)
+            e = _empty((n * (h // 2) * (w // 2), co), dt, dev)
+            L.maxpool2(full, e, n, h, w, co)
+            h, w, c = h // 2, w // 2, co
+        return e, h, w
+
+    def decode(self, e, n, h, w, backend=L.GEMM_AUTO):
+        """Decoder (genconvit_ed.py:43-61): -> NHWC [N, 32h, 32w, 3]."""
+        return _run_convt_stack(e, self.dec, n, h, w, L.ACT_RELU, self.dt, self.dev, backend)
+
+    def forward(self, x, backend=L.GEMM_AUTO):
+        """GenConViTED.forward (genconvit_ed.py:77-89) -> fp32 logits [N,2].
+
+        The two backbone passes share weights, so decoded and original frames run as
+        one 2N-image batch; rows [0,N) are the decoded images (cat order x1=decoded, x2=images).
+        """
+        dev, dt = self.dev, self.dt
+        n, _, hh, ww = x.shape
+        e, h, w = self.encode(x, backend)
+        dec, dh, dw = self.decode(e, n, h, w, backend)
+        assert (dh, dw) == (hh, ww)
+        th, tw = hh // 4, ww // 4
+        a0 = _empty((2 * n * th * tw, 48), dt, dev)
+        L.stem_patchify_nhwc(dec, a0, n, hh, ww)
+        L.stem_patchify_nchw(x, a0[n * th * tw:], n, hh, ww)
+        cat = _empty((n, 2000), dt, dev)
+        self.backbone.forward_tokens(a0, [(2 * n, th, tw)], [(0, n, cat, 2000), (n, n, cat[:, 1000:], 2000)],
+                                     L.ACT_GELU, backend)
+        return _heads(cat, n, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, L.ACT_GELU, dt, dev, backend)
+
+
+class PackedVAE:
+    """Network B (reference model/genconvit_vae.py:90-116)."""
+
+    def __init__(self, sd, dev, dt, with_var=False):
+        self.dev, self.dt = dev, dt
+        self.enc = []
+        for i in (0, 3, 6, 9):
+            # BatchNorm2d in eval mode (running stats, eps 1e-5) folded into the conv (genconvit_vae.py:16-29)
+            b = f"encoder.features.{i + 1}."
+            scale = sd[b + "weight"].float() / torch.sqrt(sd[b + "running_var"].float() + 1e-5)
+            w = sd[f"encoder.features.{i}.weight"].float() * scale.view(-1, 1, 1, 1)
+            bias = (sd[f"encoder.features.{i}.bias"].float() - sd[b + "running_mean"].float()) * scale + sd[b + "bias"].float()
+            if i == 0:
+                self.enc0_w, self.enc0_b = _f32(w, dev), _f32(bias, dev)
+            else:
+                self.enc.append((_pack_conv3x3(w, dev, dt), _f32(bias, dev)))
+        self.mu_w, self.mu_b = self._pack_latent(sd["encoder.mu.weight"], sd["encoder.mu.bias"])
+        self.var_w = self.var_b = None
+        self._var_src = (sd["encoder.var.weight"], sd["encoder.var.bias"]) if with_var else None
+        self.dec = [_pack_convt(sd[f"decoder.features.{i}.weight"], sd[f"decoder.features.{i}.bias"], dev, dt)
+                    for i in (0, 2, 4, 6)]
+        pre = "convnext_backbone."
+        self.backbone = PackedConvNeXt({k[len(pre):]: v for k, v in sd.items()
+                                        if k.startswith(pre) and not k.startswith(pre + "patch_embed.")}, dev, dt)
+        self.fc_w, self.fc_b = _cd(sd["fc.weight"], dev, dt), _f32(sd["fc.bias"], dev)
+        self.fc2_w, self.fc2_b = _cd(sd["fc2.weight"], dev, dt), _f32(sd["fc2.bias"], dev)
+
+    def _pack_latent(self, w, b):
+        """mu/var Linear(25088 -> 12544): the reference flattens NCHW on both sides
+        (input c*196+hw, genconvit_vae.py:53; output c*49+hw, :83).  Activations here are NHWC,
+        so permute rows to (hw7, c7) and columns to (hw14, c14) once."""
+        dev, dt = self.dev, self.dt
+        w = w.detach().to(dev)
+        w = w.view(256, 49, 128, 196).permute(1, 0, 3, 2).to(dt).reshape(12544, 25088).contiguous()
+        return w, _f32(b.view(256, 49).t().reshape(-1), dev)
+
+    def encode_features(self, x, backend=L.GEMM_AUTO):
+        """Encoder.features (genconvit_vae.py:15-31) -> [N, 14*14*128] NHWC-flattened."""
+        dev, dt = self.dev, self.dt
+        n, _, hh, ww = x.shape
+        h, w, c = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1, 16
+        e = _empty((n * h * w, c), dt, dev)
+        L.conv3x3_first(x, e, self.enc0_w, self.enc0_b, 2, L.ACT_LEAKY, False, n, hh, ww)
+        for wt, bias in self.enc:
+            co = wt.shape[0]
+            h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            a = _empty((n * h2 * w2, 9 * c), dt, dev)
+            L.im2col3x3(e, a, n, h, w, c, 2)
+            e = _empty((n * h2 * w2, co), dt, dev)
+            L.gemm(a, wt, e, n * h2 * w2, co, 9 * c, bias=bias, act=L.ACT_LEAKY, backend=backend)
+            h, w, c = h2, w2, co
+        return e.view(n, h * w * c)
+
+    def latent(self, feat, eps, mu_out=None, backend=L.GEMM_AUTO):
+        """mu GEMM with the reparameterisation fused in the epilogue:
+        z = eps * exp(0.5*mu) + mu  (genconvit_vae.py:43-49; std comes from ``mu``, evaluated once).
+        ``eps`` is [N,12544] fp32 in the reference's latent order; z is NHWC [N*49, 256]."""
+        n = feat.shape[0]
+        z = _empty((n * 49, 256), self.dt, self.dev)
+        L.gemm(feat, self.mu_w, z, n, 12544, 25088, bias=self.mu_b, eps=eps, eps_c=256, eps_hw=49, mu_out=mu_out,
+               ldd=12544, backend=backend)
+        return z
+
+    def kl(self, feat, mu):
+        """The ``Encoder.kl`` side effect (genconvit_vae.py:56,58); needs the ``var`` GEMM, so it is
+        computed only on request.  ``mu``: fp32 [N,12544] (column order is irrelevant for the sum)."""
+        if self.var_w is None:
+            if self._var_src is None:
+                raise L.GcvError("kl requested but the var weights were not kept (with_var=False)")
+            self.var_w, self.var_b = self._pack_latent(*self._var_src)
+        n = feat.shape[0]
+        var = _empty((n, 12544), torch.float32, self.dev)
+        L.gemm(feat, self.var_w, var, n, 12544, 25088, bias=self.var_b, out_f32=self.dt != torch.float32)
+        return 0.5 * torch.mean(-0.5 * torch.sum(1 + var - mu ** 2 - var.exp(), dim=1), dim=0)
+
+    def forward(self, x, eps, want_xhat=False, want_kl=False, backend=L.GEMM_AUTO):
+        """GenConViTVAE.forward (genconvit_vae.py:107-116) -> (fp32 logits [N,2], x_hat224 | None, kl | None).
+
+        The backbone runs on x at 224x224 and on the 112x112 reconstruction; both passes
+        share one set of GEMM launches over the concatenated tokens."""
+        dev, dt = self.dev, self.dt
+        n, _, hh, ww = x.shape
+        feat = self.encode_features(x, backend)
+        mu = _empty((n, 12544), torch.float32, dev) if want_kl else None
+        z = self.latent(feat, eps, mu, backend)
+        xhat, h2, w2 = _run_convt_stack(z, self.dec, n, 7, 7, L.ACT_LEAKY, dt, dev, backend)
+        t1 = (hh // 4, ww // 4)
+        t2 = (h2 // 4, w2 // 4)
+        m1 = n * t1[0] * t1[1]
+        a0 = _empty((m1 + n * t2[0] * t2[1], 48), dt, dev)
+        L.stem_patchify_nchw(x, a0, n, hh, ww)
+        L.stem_patchify_nhwc(xhat, a0[m1:], n, h2, w2)
+        cat = _empty((n, 2000), dt, dev)
+        self.backbone.forward_tokens(a0, [(n, *t1), (n, *t2)], [(0, n, cat, 2000), (n, n, cat[:, 1000:], 2000)],
+                                     L.ACT_RELU, backend)
+        logits = _heads(cat, n, self.fc_w, self.fc_b, self.fc2_w, self.fc2_b, L.ACT_RELU, dt, dev, backend)
+        xhat224 = None
+        if want_xhat:
+            xhat224 = _empty((n, 3, 2 * h2, 2 * w2), torch.float32, dev)
+            L.resize2x_to_nchw(xhat, xhat224, n, h2, w2, 3)
+        return logits, xhat224, (self.kl(feat, mu) if want_kl else None)
+
+
+def score_videos(logits, n_nets, n_frames, frames_per_video):
+    """Batched pred_vid scoring (model/pred_func.py:111-131): -> (mean [V,2], cls [V] int32, val [V]) on device."""
+    v = n_frames // frames_per_video
+    dev = logits.device
+    mean = torch.empty((v, 2), dtype=torch.float32, device=dev)
+    cls = torch.empty((v,), dtype=torch.int32, device=dev)
+    val = torch.empty((v,), dtype=torch.float32, device=dev)
+    L.score_videos(logits, n_nets, n_frames, frames_per_video, mean, cls, val)
+    return mean, cls, val

@@ -1,0 +1,210 @@
+"""ctypes binding of libgenconvit_b200.so (the C ABI in include/genconvit_b200.h).
+
+The product path has no CPU or library fallback: if the shared library is
+missing, or a kernel call fails, this raises.  torch is used only for device
+memory (``tensor.data_ptr()``) and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgenconvit_b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY = 0, 1, 2, 3
+STORE_ROWS, STORE_PIXEL_SHUFFLE2 = 0, 1
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
+
+DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+EXPORTS = [
+    "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_dwconv7_ln", "gcv_ln_patchify2",
+    "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+]
+
+
+class Epilogue(C.Structure):
+    """Mirror of ``gcv_epilogue``."""
+    _fields_ = [
+        ("bias", C.c_void_p), ("act", C.c_int32), ("gamma", C.c_void_p), ("residual", C.c_void_p),
+        ("ldr", C.c_int64), ("eps", C.c_void_p), ("eps_c", C.c_int32), ("eps_hw", C.c_int32),
+        ("mu_out", C.c_void_p), ("store", C.c_int32), ("ps_h", C.c_int32), ("ps_w", C.c_int32),
+        ("ps_co", C.c_int32), ("ldd", C.c_int64), ("out_f32", C.c_int32),
+    ]
+
+
+class GcvError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GcvError(f"{LIB_PATH} not found: build it with `python -m genconvit_b200.build` "
+                       "(there is no CPU / eager fallback for the GenConViT forward)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.gcv_abi_version.restype = C.c_int
+    lib.gcv_last_error.restype = C.c_char_p
+    lib.gcv_device_supported.argtypes = [i32]
+    lib.gcv_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, i64, i64, i64, C.POINTER(Epilogue), vp]
+    lib.gcv_dwconv7_ln.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
+    lib.gcv_ln_patchify2.argtypes = [i32, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
+    lib.gcv_stem_patchify_nchw.argtypes = [i32, vp, vp, i32, i32, i32, vp]
+    lib.gcv_stem_patchify_nhwc.argtypes = [i32, vp, vp, i32, i32, i32, vp]
+    lib.gcv_layernorm_rows.argtypes = [i32, vp, vp, vp, vp, f32, i64, i32, vp]
+    lib.gcv_pool_ln.argtypes = [i32, vp, vp, vp, vp, f32, i32, i32, i32, vp]
+    lib.gcv_conv3x3_first.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.gcv_im2col3x3.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_score_videos.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("gcv_last_error",):
+            fn.restype = C.c_int
+    if lib.gcv_abi_version() != 1:
+        raise GcvError("libgenconvit_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().gcv_last_error().decode(errors="replace")
+        raise GcvError(f"{what} failed (status {rc}): {msg}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise GcvError(f"{what}: tensor is on {t.device}; the GenConViT forward only runs on a CUDA (sm_100a) device "
+                       "-- there is no CPU fallback")
+
+
+# ---- launch counter (bench.py reports how many of our kernels ran in the timed region) ----
+launches = 0
+
+
+def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, gamma=None, residual=None,
+         ldr=None, eps=None, eps_c=0, eps_hw=0, mu_out=None, store=STORE_ROWS, ps=(0, 0, 0), out_f32=False,
+         backend=GEMM_AUTO):
+    """D[M,N] = epilogue(A[M,K] @ B[N,K]^T); see gcv_gemm / gcv_epilogue."""
+    global launches
+    require_cuda(a, "gemm")
+    ep = Epilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.act = act
+    ep.gamma = gamma.data_ptr() if gamma is not None else None
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.ldr = ldr if ldr is not None else N
+    ep.eps = eps.data_ptr() if eps is not None else None
+    ep.eps_c, ep.eps_hw = eps_c, eps_hw
+    ep.mu_out = mu_out.data_ptr() if mu_out is not None else None
+    ep.store = store
+    ep.ps_h, ep.ps_w, ep.ps_co = ps
+    ep.ldd = ldd if ldd is not None else N
+    ep.out_f32 = 1 if out_f32 else 0
+    rc = load().gcv_gemm(backend, DTYPE_CODE[a.dtype], _p(a), lda if lda is not None else K, _p(b),
+                         ldb if ldb is not None else K, _p(d), M, N, K, C.byref(ep), _stream())
+    _check(rc, f"gcv_gemm(M={M},N={N},K={K})")
+    launches += 1
+
+
+def dwconv7_ln(x, y, taps, bias, ln_w, ln_b, eps, B, H, W, Cc):
+    global launches
+    _check(load().gcv_dwconv7_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(taps), _p(bias), _p(ln_w), _p(ln_b), eps,
+                                 B, H, W, Cc, _stream()), "gcv_dwconv7_ln")
+    launches += 1
+
+
+def ln_patchify2(x, a, ln_w, ln_b, eps, B, H, W, Cc):
+    global launches
+    _check(load().gcv_ln_patchify2(DTYPE_CODE[x.dtype], _p(x), _p(a), _p(ln_w), _p(ln_b), eps, B, H, W, Cc, _stream()),
+           "gcv_ln_patchify2")
+    launches += 1
+
+
+def stem_patchify_nchw(x, a, B, H, W):
+    global launches
+    assert x.dtype == torch.float32
+    _check(load().gcv_stem_patchify_nchw(DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()), "gcv_stem_patchify_nchw")
+    launches += 1
+
+
+def stem_patchify_nhwc(x, a, B, H, W):
+    global launches
+    _check(load().gcv_stem_patchify_nhwc(DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()), "gcv_stem_patchify_nhwc")
+    launches += 1
+
+
+def layernorm_rows(x, y, w, b, eps, rows, Cc):
+    global launches
+    _check(load().gcv_layernorm_rows(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, rows, Cc, _stream()),
+           "gcv_layernorm_rows")
+    launches += 1
+
+
+def pool_ln(x, y, w, b, eps, B, HW, Cc):
+    global launches
+    _check(load().gcv_pool_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, B, HW, Cc, _stream()), "gcv_pool_ln")
+    launches += 1
+
+
+def conv3x3_first(x, y, w, b, stride, act, pool, B, H, W):
+    global launches
+    assert x.dtype == torch.float32
+    _check(load().gcv_conv3x3_first(DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(b), stride, act, 1 if pool else 0,
+                                    B, H, W, _stream()), "gcv_conv3x3_first")
+    launches += 1
+
+
+def im2col3x3(x, a, B, H, W, Cc, stride):
+    global launches
+    _check(load().gcv_im2col3x3(DTYPE_CODE[x.dtype], _p(x), _p(a), B, H, W, Cc, stride, _stream()), "gcv_im2col3x3")
+    launches += 1
+
+
+def maxpool2(x, y, B, H, W, Cc):
+    global launches
+    _check(load().gcv_maxpool2(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_maxpool2")
+    launches += 1
+
+
+def resize2x_to_nchw(x, y, B, H, W, Cc):
+    global launches
+    _check(load().gcv_resize2x_to_nchw(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_resize2x_to_nchw")
+    launches += 1
+
+
+def nhwc_to_nchw_f32(x, y, B, H, W, Cc):
+    global launches
+    _check(load().gcv_nhwc_to_nchw_f32(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_nhwc_to_nchw_f32")
+    launches += 1
+
+
+def score_videos(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out):
+    global launches
+    require_cuda(logits, "score_videos")
+    _check(load().gcv_score_videos(_p(logits), n_nets, n_frames, fpv, _p(mean_out), _p(cls_out), _p(val_out), _stream()),
+           "gcv_score_videos")
+    launches += 1

@@ -1,0 +1,148 @@
+/*
+ * genconvit_b200 -- C ABI of the sm_100a kernel library behind the GenConViT
+ * frame-inference forward (libgenconvit_b200.so).
+ *
+ * The reference (ctxnn/GenConViT) is pure Python/PyTorch: its "FFI" for this
+ * path is the ATen operator set reached from model/genconvit_ed.py,
+ * model/genconvit_vae.py and timm's ConvNeXt.  Each entry point below names the
+ * reference operator call site(s) it replaces.  The library has no torch
+ * dependency: plain device pointers, sizes, a cudaStream_t (passed as void*),
+ * int status return (0 = ok, negative = GCV_ERR_*), no exceptions.
+ *
+ * Conventions
+ *   - activations are NHWC ("tokens x channels"), element type `dtype`
+ *     (GCV_F32 / GCV_BF16 / GCV_F16); parameter vectors (bias, gamma, LN
+ *     weight/bias, depthwise taps) are always fp32;
+ *   - GEMMs compute D[M,N] = A[M,K] * B[N,K]^T with fp32 accumulation, A and
+ *     B both K-major (row-major [rows, K] with leading dimensions lda/ldb in
+ *     elements), i.e. exactly nn.Linear with B = weight;
+ *   - all pointers are device pointers unless stated otherwise; all kernels are
+ *     enqueued on `stream` and never synchronise.
+ */
+#ifndef GENCONVIT_B200_H_
+#define GENCONVIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCV_ABI_VERSION 1
+
+enum gcv_dtype { GCV_F32 = 0, GCV_BF16 = 1, GCV_F16 = 2 };
+enum gcv_act { GCV_ACT_NONE = 0, GCV_ACT_GELU = 1, GCV_ACT_RELU = 2, GCV_ACT_LEAKY = 3 };
+enum gcv_store { GCV_STORE_ROWS = 0, GCV_STORE_PIXEL_SHUFFLE2 = 1 };
+enum gcv_backend { GCV_GEMM_AUTO = 0, GCV_GEMM_TCGEN05 = 1, GCV_GEMM_SIMT = 2 };
+
+enum gcv_status {
+  GCV_OK = 0,
+  GCV_ERR_BAD_ARG = -1,       /* shape / alignment / dtype the kernel cannot take */
+  GCV_ERR_CUDA = -2,          /* a CUDA runtime call failed; see gcv_last_error() */
+  GCV_ERR_UNSUPPORTED = -3,   /* e.g. tcgen05 path asked for on fp32 data        */
+  GCV_ERR_NO_DRIVER = -4      /* cuTensorMapEncodeTiled could not be resolved    */
+};
+
+/*
+ * Epilogue applied to the fp32 accumulator of both GEMM back ends, in this
+ * order:  v = acc + bias[n];  v = act(v);
+ *         if (eps)      { mu = v; v = eps[m, perm(n)] * exp(0.5*mu) + mu; }
+ *         if (gamma)    v = gamma[n] * v;
+ *         if (residual) v = residual[m, n] + v;
+ * and stored as `dtype` (or fp32 when out_f32 != 0) at
+ *   GCV_STORE_ROWS:           D[m*ldd + n]
+ *   GCV_STORE_PIXEL_SHUFFLE2: NHWC [B, 2H, 2W, Co] with m = (b,h,w),
+ *                             n = (i*2+j)*Co + co  ->  (b, 2h+i, 2w+j, co)
+ */
+typedef struct gcv_epilogue {
+  const float* bias;        /* [N] or NULL */
+  int32_t act;              /* gcv_act */
+  const float* gamma;       /* [N] layer scale or NULL */
+  const void* residual;     /* [M, ldr] of `dtype`, or NULL (may alias D) */
+  int64_t ldr;
+  const float* eps;         /* [M, N] fp32 VAE epsilon in the reference's latent order, or NULL */
+  int32_t eps_c;            /* latent is NHWC-ordered here: n = hw*eps_c + c; reference index = c*eps_hw + hw */
+  int32_t eps_hw;
+  float* mu_out;            /* optional [M, N] fp32 copy of mu (same column order as D), or NULL */
+  int32_t store;            /* gcv_store */
+  int32_t ps_h, ps_w, ps_co;
+  int64_t ldd;
+  int32_t out_f32;
+} gcv_epilogue;
+
+/* -- library ------------------------------------------------------------- */
+int gcv_abi_version(void);
+const char* gcv_last_error(void);          /* host string, valid until the next failing call */
+int gcv_device_supported(int device);      /* 1 when `device` is compute capability 10.x */
+
+/* -- contraction kernels --------------------------------------------------
+ * Replaces: every nn.Linear / F.linear on the path (timm Mlp fc1/fc2, head.fc;
+ * genconvit_ed.py:73-74,87; genconvit_vae.py:36,101-103,114), the patchify
+ * convolutions (timm stem 4x4 s4, downsample 2x2 s2), the im2col'd 3x3
+ * convolutions (genconvit_ed.py:14-30; genconvit_vae.py:16-28) and the k2 s2
+ * transposed convolutions (genconvit_ed.py:44-56; genconvit_vae.py:68-77).
+ * backend: GCV_GEMM_TCGEN05 = TMA-fed tcgen05.mma with TMEM accumulators
+ * (bf16/fp16 only; K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned
+ * bases); GCV_GEMM_SIMT = fp32-FMA kernel (any dtype/shape); AUTO picks
+ * tcgen05 whenever its constraints hold.
+ */
+int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
+             void* D, int64_t M, int64_t N, int64_t K, const gcv_epilogue* ep, void* stream);
+
+/* -- ConvNeXt memory-bound kernels ----------------------------------------
+ * gcv_dwconv7_ln: timm ConvNeXtBlock.conv_dw (7x7, pad 3, groups=C, bias) fused
+ *   with ConvNeXtBlock.norm (LayerNorm over C, eps).  x,y: [B,H,W,C]; taps: [49,C].
+ * gcv_ln_patchify2: stage downsample = LayerNorm2d(C) then the im2col of the
+ *   2x2 s2 conv: x [B,H,W,C] -> A [B*(H/2)*(W/2), 4C], column (kh*2+kw)*C + c.
+ * gcv_stem_patchify_nchw / _nhwc: im2col of the 4x4 s4 stem conv from the fp32
+ *   NCHW frames / from an NHWC image of `dtype`: -> A [B*(H/4)*(W/4), 48],
+ *   column (kh*4+kw)*3 + c.
+ * gcv_layernorm_rows: LayerNorm over the last dimension of [rows, C] (stem.1).
+ * gcv_pool_ln: head.global_pool + head.norm: [B,HW,C] -> LN(mean over HW) [B,C].
+ */
+int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias,
+                   const float* ln_w, const float* ln_b, float eps,
+                   int B, int H, int W, int C, void* stream);
+int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps,
+                     int B, int H, int W, int C, void* stream);
+int gcv_stem_patchify_nchw(int dtype, const float* x, void* a, int B, int H, int W, void* stream);
+int gcv_stem_patchify_nhwc(int dtype, const void* x, void* a, int B, int H, int W, void* stream);
+int gcv_layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps,
+                       int64_t rows, int C, void* stream);
+int gcv_pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, float eps,
+                int B, int HW, int C, void* stream);
+
+/* -- autoencoder kernels ----------------------------------------------------
+ * gcv_conv3x3_first: first 3x3 conv (Cin=3 -> 16, pad 1) straight from the fp32
+ *   NCHW frames, w: [16][3][3][3] fp32 (OIHW), followed by `act` and, when
+ *   pool != 0, a 2x2 max-pool.  stride 1 + ReLU + pool = genconvit_ed.py:14-16;
+ *   stride 2 + (BatchNorm folded into w,b by the host) + LeakyReLU =
+ *   genconvit_vae.py:16-18.  y: NHWC.
+ * gcv_im2col3x3: x [B,H,W,C] -> A [B*Ho*Wo, 9C], column (kh*3+kw)*C + c, pad 1.
+ * gcv_maxpool2: NHWC 2x2 s2 max-pool (genconvit_ed.py:16,20,24,28,32).
+ * gcv_resize2x_to_nchw: the returned x_hat: bilinear (align_corners=False) 2x
+ *   upscale of NHWC `dtype` [B,H,W,3] to NCHW fp32 [B,3,2H,2W]
+ *   (genconvit_vae.py:105,116 -- antialias is a no-op when upscaling).
+ * gcv_nhwc_to_nchw_f32: layout/dtype conversion for tensors handed back to torch.
+ */
+int gcv_conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b,
+                      int stride, int act, int pool, int B, int H, int W, void* stream);
+int gcv_im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, void* stream);
+int gcv_maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
+int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
+int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
+
+/* -- scoring ----------------------------------------------------------------
+ * model/pred_func.py:111-131 (pred_vid after the forward + max_prediction_value),
+ * batched over videos: logits [n_nets*n_frames, 2] fp32 with each net's rows
+ * contiguous (GenConViT.forward's cat(dim=0), genconvit.py:74); video v owns
+ * frames [v*fpv, (v+1)*fpv) of every net.  Writes per video the mean sigmoid
+ * [V,2], the argmax class and the reported score.
+ */
+int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video,
+                     float* mean_out, int32_t* cls_out, float* val_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENCONVIT_B200_H_ */

@@ -1,0 +1,56 @@
+"""``GenConViT`` wrapper -- drop-in for reference model/genconvit.py:7-75."""
+import torch
+import torch.nn as nn
+
+from .genconvit_ed import GenConViTED
+from .genconvit_vae import GenConViTVAE
+
+
+def _load_into(module, name):
+    """weight/{name}.pth, cwd-relative, raw state_dict or {'state_dict': ...} (reference :16-21)."""
+    ckpt = torch.load(f"weight/{name}.pth", map_location=torch.device("cpu"))
+    sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+    module.load_state_dict(sd)
+    module.eval()
+    # The reference keeps the whole checkpoint alive as self.checkpoint_ed/vae (2.6 GiB of host RAM
+    # for the VAE); only its non-tensor metadata is kept here.
+    return {k: v for k, v in ckpt.items() if k != "state_dict" and not torch.is_tensor(v)} if "state_dict" in ckpt else {}
+
+
+class GenConViT(nn.Module):
+    def __init__(self, config, ed, vae, net, fp16):
+        super().__init__()
+        self.net = net
+        self.fp16 = fp16
+        try:
+            if net != "vae":
+                self.model_ed = GenConViTED(config)
+                self.checkpoint_ed = _load_into(self.model_ed, ed)
+            if net != "ed":
+                self.model_vae = GenConViTVAE(config)
+                self.checkpoint_vae = _load_into(self.model_vae, vae)
+        except FileNotFoundError:
+            if net == "ed":
+                raise Exception(f"Error: weight/{ed}.pth file not found.")
+            if net == "vae":
+                raise Exception(f"Error: weight/{vae}.pth file not found.")
+            raise Exception("Error: Model weights file not found.")
+        if fp16:
+            self.half()
+
+    def set_compute_dtype(self, dt):
+        for m in (getattr(self, "model_ed", None), getattr(self, "model_vae", None)):
+            if m is not None:
+                m.set_compute_dtype(dt)
+        return self
+
+    def forward(self, x, eps=None):
+        """'ed' -> [N,2]; 'vae' -> [N,2]; otherwise ED rows then VAE rows -> [2N,2] (reference :66-75).
+        The VAE's returned image is discarded by the reference here, so it is not computed."""
+        if self.net == "ed":
+            return self.model_ed(x)
+        if self.net == "vae":
+            return self.model_vae._forward(x, eps, want_xhat=False)[0]
+        x1 = self.model_ed(x)
+        x2 = self.model_vae._forward(x, eps, want_xhat=False)[0]
+        return torch.cat((x1, x2), dim=0)

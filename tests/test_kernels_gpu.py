@@ -1,0 +1,289 @@
+"""GPU: every kernel of libgenconvit_b200.so, called through the C ABI, against a plain torch
+fp32 restatement of the same operator on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# the torch restatements must be true fp32 (cuDNN convs default to TF32)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+DEV = "cuda"
+DTYPES = [torch.float32, torch.bfloat16, torch.float16]
+TOL = {torch.float32: 2e-5, torch.bfloat16: 2e-2, torch.float16: 3e-3}
+
+
+def _lib():
+    from genconvit_b200 import lib
+    lib.load()
+    return lib
+
+
+def _rand(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def _close(got, want, tol, what=""):
+    err = (got.float() - want.float()).abs().max().item()
+    ref = want.float().abs().max().item()
+    assert err <= tol * max(1.0, ref), f"{what}: max|d|={err:.3e} (ref max {ref:.3e}, tol {tol})"
+
+
+# --------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [(128, 128, 64), (300, 200, 96), (1000, 96, 384), (257, 1000, 768), (64, 12, 16), (100, 96, 48),
+               (4096, 1536, 384), (15, 500, 2000), (777, 384, 1536), (50, 256, 32)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_tcgen05_plain(shape, dtype):
+    L = _lib()
+    M, N, K = shape
+    a, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    d = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, d, M, N, K, out_f32=True, backend=L.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    _close(d, a.float() @ b.float().t(), 1e-4, f"tcgen05 {shape}")
+
+
+@pytest.mark.parametrize("block_n", [32, 64, 96, 128, 192, 256])
+def test_gemm_tcgen05_every_tile_width(block_n):
+    L = _lib()
+    M, N, K = 1000, 700, 448
+    a, b = _rand(M, K, dtype=torch.bfloat16, seed=3), _rand(N, K, dtype=torch.bfloat16, seed=4, scale=K ** -0.5)
+    d = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, d, M, N, K, out_f32=True, backend=1000 + block_n)
+    torch.cuda.synchronize()
+    _close(d, a.float() @ b.float().t(), 1e-4, f"block_n={block_n}")
+
+
+def test_gemm_tcgen05_many_tiles_persistent():
+    """More tiles than SMs: every CTA loops over several tiles and both TMEM stages wrap."""
+    L = _lib()
+    M, N, K = 148 * 128 * 3 + 17, 384, 96
+    a, b = _rand(M, K, dtype=torch.bfloat16, seed=5), _rand(N, K, dtype=torch.bfloat16, seed=6, scale=K ** -0.5)
+    d = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    L.gemm(a, b, d, M, N, K, backend=L.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    _close(d, a.float() @ b.float().t(), 1e-2, "persistent")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_gemm_epilogues(dtype, backend):
+    L = _lib()
+    be = L.GEMM_SIMT if backend == "simt" else L.GEMM_AUTO
+    tol = TOL[dtype]
+    M, N, K = 333, 192, 96
+    a, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias, gamma = _rand(N, seed=3), _rand(N, seed=4)
+    acc = a.float() @ b.float().t() + bias
+    # bias + GELU(erf)
+    d = torch.empty((M, N), device=DEV, dtype=dtype)
+    L.gemm(a, b, d, M, N, K, bias=bias, act=L.ACT_GELU, backend=be)
+    _close(d, F.gelu(acc), tol, "gelu")
+    # ReLU / LeakyReLU(0.01)
+    L.gemm(a, b, d, M, N, K, bias=bias, act=L.ACT_RELU, backend=be)
+    _close(d, F.relu(acc), tol, "relu")
+    L.gemm(a, b, d, M, N, K, bias=bias, act=L.ACT_LEAKY, backend=be)
+    _close(d, F.leaky_relu(acc, 0.01), tol, "leaky")
+    # residual + gamma * (acc + bias), in place on the residual
+    res = _rand(M, N, dtype=dtype, seed=5)
+    want = res.float() + gamma * acc
+    L.gemm(a, b, res, M, N, K, bias=bias, gamma=gamma, residual=res, ldr=N, backend=be)
+    _close(res, want, tol, "gamma+residual")
+    # column window of a wider buffer (ldd) + fp32 output
+    wide = torch.zeros((M, 2 * N + 8), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, wide[:, N:], M, N, K, bias=bias, ldd=2 * N + 8, out_f32=dtype != torch.float32, backend=be)
+    _close(wide[:, N:2 * N], acc, tol if dtype == torch.float32 else 1e-4, "ldd window")
+    assert wide[:, :N].abs().max().item() == 0 and wide[:, 2 * N:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cfg", [(2, 7, 7, 256, 128), (1, 14, 14, 64, 32), (2, 5, 3, 16, 3), (1, 28, 28, 32, 16)])
+def test_gemm_pixel_shuffle_is_conv_transpose(cfg, dtype):
+    """k2 s2 ConvTranspose2d as GEMM + pixel-shuffle store (reference genconvit_ed.py:44-56)."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_convt
+    B, H, W, ci, co = cfg
+    x = _rand(B, ci, H, W, seed=1)
+    w, bias = _rand(ci, co, 2, 2, seed=2, scale=ci ** -0.5), _rand(co, seed=3)
+    want = F.leaky_relu(F.conv_transpose2d(x, w, bias, stride=2), 0.01).permute(0, 2, 3, 1)
+    wp, bp = _pack_convt(w, bias, DEV, dtype)
+    tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, ci).to(dtype).contiguous()
+    out = torch.empty((B, 2 * H, 2 * W, co), device=DEV, dtype=dtype)
+    L.gemm(tokens, wp, out, B * H * W, 4 * co, ci, bias=bp, act=L.ACT_LEAKY, store=L.STORE_PIXEL_SHUFFLE2, ps=(H, W, co))
+    _close(out, want, TOL[dtype], f"convT {cfg}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_reparam_epilogue(dtype):
+    """z = eps*exp(0.5*mu) + mu with eps given in the reference's (c*hw + hw) latent order."""
+    L = _lib()
+    M, K, C, HW = 5, 64, 16, 4
+    N = C * HW
+    a, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias, eps = _rand(N, seed=3), _rand(M, N, seed=4)
+    mu = a.float() @ b.float().t() + bias                       # columns n = hw*C + c
+    eps_nhwc = eps.view(M, C, HW).transpose(1, 2).reshape(M, N)  # reference index c*HW + hw -> n
+    want = eps_nhwc * torch.exp(0.5 * mu) + mu
+    z = torch.empty((M, N), device=DEV, dtype=dtype)
+    mu_out = torch.empty((M, N), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, z, M, N, K, bias=bias, eps=eps, eps_c=C, eps_hw=HW, mu_out=mu_out)
+    _close(z, want, TOL[dtype], "reparam")
+    _close(mu_out, mu, 1e-4, "mu_out")
+
+
+# --------------------------------------------------------------------------- ConvNeXt kernels
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cfg", [(2, 56, 56, 96), (1, 28, 28, 192), (2, 14, 14, 384), (2, 7, 7, 768), (1, 3, 3, 768),
+                                 (1, 9, 13, 96)])
+def test_dwconv7_ln(cfg, dtype):
+    L = _lib()
+    B, H, W, C = cfg
+    x = _rand(B, H, W, C, dtype=dtype, seed=1)
+    w, bias = _rand(C, 1, 7, 7, seed=2, scale=1 / 7), _rand(C, seed=3, scale=0.1)
+    lw, lb = _rand(C, seed=4).abs() + 0.5, _rand(C, seed=5, scale=0.1)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (C,), lw, lb, 1e-6)
+    out = torch.full_like(x, float("nan"))
+    L.dwconv7_ln(x, out, w.reshape(C, 49).t().contiguous(), bias, lw, lb, 1e-6, B, H, W, C)
+    _close(out, want, TOL[dtype] * 2, f"dwconv {cfg}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cfg", [(2, 56, 56, 96), (1, 7, 7, 384), (2, 14, 14, 192)])
+def test_ln_patchify2(cfg, dtype):
+    L = _lib()
+    B, H, W, C = cfg
+    x = _rand(B, H, W, C, dtype=dtype, seed=1)
+    lw, lb = _rand(C, seed=4).abs() + 0.5, _rand(C, seed=5, scale=0.1)
+    ln = F.layer_norm(x.float(), (C,), lw, lb, 1e-6)
+    Ho, Wo = H // 2, W // 2
+    want = ln[:, :2 * Ho, :2 * Wo].reshape(B, Ho, 2, Wo, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * Ho * Wo, 4 * C)
+    out = torch.full((B * Ho * Wo, 4 * C), float("nan"), device=DEV, dtype=dtype)
+    L.ln_patchify2(x, out, lw, lb, 1e-6, B, H, W, C)
+    _close(out, want, TOL[dtype], f"ln_patchify2 {cfg}")
+    # and it is the im2col of the reference's 2x2 s2 conv: GEMM with the packed weight == F.conv2d
+    wc = _rand(2 * C, C, 2, 2, seed=6, scale=(4 * C) ** -0.5)
+    conv = F.conv2d(ln[:, :2 * Ho, :2 * Wo].permute(0, 3, 1, 2), wc, stride=2).permute(0, 2, 3, 1).reshape(-1, 2 * C)
+    _close(want @ wc.permute(0, 2, 3, 1).reshape(2 * C, -1).t(), conv, 1e-4, "patchify order")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_stem_patchify_both_layouts(dtype):
+    L = _lib()
+    B, H, W = 2, 32, 24
+    x = _rand(B, 3, H, W, seed=1)
+    want = F.unfold(x, 4, stride=4).view(B, 3, 4, 4, -1).permute(0, 4, 2, 3, 1).reshape(B * (H // 4) * (W // 4), 48)
+    out = torch.full((want.shape[0], 48), float("nan"), device=DEV, dtype=dtype)
+    L.stem_patchify_nchw(x, out, B, H, W)
+    _close(out, want, TOL[dtype], "stem nchw")
+    xn = x.permute(0, 2, 3, 1).contiguous().to(dtype)
+    out2 = torch.full_like(out, float("nan"))
+    L.stem_patchify_nhwc(xn, out2, B, H, W)
+    _close(out2, want, TOL[dtype], "stem nhwc")
+    # column order matches the packed stem weight: GEMM == conv 4x4 s4
+    w = _rand(96, 3, 4, 4, seed=2, scale=48 ** -0.5)
+    conv = F.conv2d(x, w, stride=4).permute(0, 2, 3, 1).reshape(-1, 96)
+    _close(want @ w.permute(0, 2, 3, 1).reshape(96, 48).t(), conv, 1e-4, "stem order")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [96, 768, 1536])
+def test_layernorm_rows_and_pool_ln(C, dtype):
+    L = _lib()
+    rows = 77
+    x = _rand(rows, C, dtype=dtype, seed=1) + 0.5
+    lw, lb = _rand(C, seed=4).abs() + 0.5, _rand(C, seed=5, scale=0.1)
+    out = torch.full_like(x, float("nan"))
+    L.layernorm_rows(x, out, lw, lb, 1e-6, rows, C)
+    _close(out, F.layer_norm(x.float(), (C,), lw, lb, 1e-6), TOL[dtype], "layernorm_rows")
+    B, HW = 7, 11
+    xp = _rand(B, HW, C, dtype=dtype, seed=2)
+    pooled = torch.full((B, C), float("nan"), device=DEV, dtype=dtype)
+    L.pool_ln(xp, pooled, lw, lb, 1e-6, B, HW, C)
+    _close(pooled, F.layer_norm(xp.float().mean(1), (C,), lw, lb, 1e-6), TOL[dtype], "pool_ln")
+
+
+# --------------------------------------------------------------------------- autoencoder kernels
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv3x3_first_variants(dtype):
+    L = _lib()
+    B, H, W = 2, 20, 28
+    x = _rand(B, 3, H, W, seed=1)
+    w, b = _rand(16, 3, 3, 3, seed=2, scale=27 ** -0.5), _rand(16, seed=3, scale=0.1)
+    # ED: stride 1 + ReLU + maxpool2
+    want = F.max_pool2d(F.relu(F.conv2d(x, w, b, padding=1)), 2).permute(0, 2, 3, 1)
+    out = torch.full((B, H // 2, W // 2, 16), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_first(x, out, w, b, 1, L.ACT_RELU, True, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3 s1 relu pool")
+    # VAE: stride 2 + LeakyReLU
+    want = F.leaky_relu(F.conv2d(x, w, b, stride=2, padding=1), 0.01).permute(0, 2, 3, 1)
+    out = torch.full((B, H // 2, W // 2, 16), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_first(x, out, w, b, 2, L.ACT_LEAKY, False, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3 s2 leaky")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("stride", [1, 2])
+def test_im2col3x3_is_conv(stride, dtype):
+    L = _lib()
+    from genconvit_b200.engine import _pack_conv3x3
+    B, H, W, C, Co = 2, 14, 10, 16, 32
+    x = _rand(B, H, W, C, dtype=dtype, seed=1)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    a = torch.full((B * Ho * Wo, 9 * C), float("nan"), device=DEV, dtype=dtype)
+    L.im2col3x3(x, a, B, H, W, C, stride)
+    w = _rand(Co, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    _close(a.float() @ _pack_conv3x3(w, DEV, torch.float32).t(), want, 1e-4, "im2col order")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool2_resize_and_layout(dtype):
+    L = _lib()
+    B, H, W, C = 2, 12, 10, 16
+    x = _rand(B, H, W, C, dtype=dtype, seed=1)
+    out = torch.empty((B, H // 2, W // 2, C), device=DEV, dtype=dtype)
+    L.maxpool2(x, out, B, H, W, C)
+    assert torch.equal(out.float(), F.max_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+    img = _rand(B, 16, 12, 3, dtype=dtype, seed=2)
+    up = torch.empty((B, 3, 32, 24), device=DEV, dtype=torch.float32)
+    L.resize2x_to_nchw(img, up, B, 16, 12, 3)
+    want = F.interpolate(img.float().permute(0, 3, 1, 2), size=(32, 24), mode="bilinear", align_corners=False,
+                         antialias=True)
+    _close(up, want, 1e-5, "resize2x")
+    nchw = torch.empty((B, 3, 16, 12), device=DEV, dtype=torch.float32)
+    L.nhwc_to_nchw_f32(img, nchw, B, 16, 12, 3)
+    assert torch.equal(nchw, img.float().permute(0, 3, 1, 2))
+
+
+def test_score_videos_matches_pred_func_semantics():
+    from genconvit_b200 import engine
+    from oracle import nets
+    n_nets, fpv, V = 2, 15, 5
+    logits = _rand(n_nets * V * fpv, 2, seed=9)
+    mean, cls, val = engine.score_videos(logits, n_nets, V * fpv, fpv)
+    lg = logits.cpu().view(n_nets, V, fpv, 2)
+    for v in range(V):
+        want_cls, want_val = nets.pred_vid(lg[:, v].reshape(-1, 2))
+        assert int(cls[v]) == want_cls and abs(float(val[v]) - want_val) < 1e-6
+    # tie -> else branch, class 0
+    tie = torch.zeros(4, 2, device=DEV)
+    _, cls, val = engine.score_videos(tie, 1, 4, 4)
+    assert int(cls[0]) == 0 and abs(float(val[0]) - 0.5) < 1e-7
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    L = _lib()
+    x = torch.zeros(4, 10, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(L.GcvError):
+        L.gemm(x, x, x, 4, 4, 10, backend=L.GEMM_TCGEN05)          # K % 8 != 0
+    with pytest.raises(L.GcvError):
+        L.dwconv7_ln(x, x, x, x, x, x, 1e-6, 1, 2, 2, 10)           # C % 32 != 0
+    with pytest.raises(L.GcvError):
+        L.gemm(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 4), 4, 4, 8)   # CPU tensors: no fallback

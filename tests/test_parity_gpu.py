@@ -1,0 +1,237 @@
+"""GPU: the drop-in ``model`` package (CUDA kernels behind the reference's module API) against
+the CPU oracle and the committed golden vectors, on the same seeded inputs and weights.
+
+Tolerances are BASELINE.json's: max-abs logit error <= 1e-4 in the fp32 mode, <= 2e-2 in
+bf16/fp16, and the same real/fake decision on every frame.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+TOL = {"fp32": 1e-4, "bf16": 2e-2, "fp16": 2e-2}
+
+
+def _config():
+    from model.config import load_config
+    return load_config()
+
+
+@pytest.fixture(scope="module")
+def ed_model(sd_ed):
+    from model.genconvit_ed import GenConViTED
+    m = GenConViTED(_config()).eval()
+    m.load_state_dict(sd_ed, strict=True)
+    return m.to(DEV)
+
+
+@pytest.fixture(scope="module")
+def vae_model(sd_vae):
+    from model.genconvit_vae import GenConViTVAE
+    m = GenConViTVAE(_config()).eval()
+    m.load_state_dict(sd_vae, strict=True)
+    return m.to(DEV)
+
+
+def _same_decisions(a, b):
+    return torch.equal(a.argmax(1).cpu(), b.argmax(1).cpu())
+
+
+def test_convnext_backbone_fp32_matches_oracle(ed_model, sd_ed):
+    from oracle import backbones
+    from oracle.weights import synthetic_frames
+    x = synthetic_frames(2, 11)
+    with torch.no_grad():
+        want = backbones.convnext_forward(sd_ed, "backbone.", x)
+        got = ed_model.backbone(x.to(DEV))
+        x112 = synthetic_frames(2, 12, 112)
+        want112 = backbones.convnext_forward(sd_ed, "backbone.", x112)
+        got112 = ed_model.backbone(x112.to(DEV))
+    assert (got.cpu() - want).abs().max().item() <= 1e-4
+    assert (got112.cpu() - want112).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+def test_ed_matches_reference_golden(ed_model, sd_ed, golden, mode):
+    """BASELINE config 0 shape: GenConViT-ED forward, random-init, vs the reference's own output."""
+    from oracle.weights import synthetic_frames
+    g = golden("ed")
+    x = synthetic_frames(g["n"], g["meta"]["seed"]).to(DEV)
+    ed_model.set_compute_dtype(mode)
+    with torch.no_grad():
+        got = ed_model(x).float().cpu()
+    err = (got - g["logits"]).abs().max().item()
+    assert err <= TOL[mode], f"ED {mode}: max|dlogit| = {err:.3e}"
+    assert _same_decisions(got, g["logits"])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_ed_15_frame_video_vs_oracle(ed_model, sd_ed, mode):
+    from oracle import nets
+    from oracle.weights import synthetic_frames
+    x = synthetic_frames(15, 21)
+    with torch.no_grad():
+        want = nets.ed_forward(sd_ed, x)
+        got = ed_model.set_compute_dtype(mode)(x.to(DEV)).float().cpu()
+    err = (got - want).abs().max().item()
+    assert err <= TOL[mode], f"ED N=15 {mode}: {err:.3e}"
+    assert _same_decisions(got, want)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp16"])
+def test_vae_matches_reference_golden(vae_model, golden, mode):
+    from oracle.weights import synthetic_eps, synthetic_frames
+    g = golden("vae")
+    x = synthetic_frames(g["n"], g["frames_seed"]).to(DEV)
+    eps = synthetic_eps(g["n"], g["eps_seed"]).to(DEV)
+    vae_model.set_compute_dtype(mode)
+    with torch.no_grad():
+        logits, xhat = vae_model(x, eps=eps)
+    err = (logits.float().cpu() - g["logits"]).abs().max().item()
+    assert err <= TOL[mode], f"VAE {mode}: max|dlogit| = {err:.3e}"
+    assert _same_decisions(logits.float(), g["logits"])
+    assert xhat.shape == (g["n"], 3, 224, 224)
+    xerr = (xhat.float().cpu()[:, :, ::37, ::41] - g["xhat224_sample"]).abs().max().item()
+    assert xerr <= (1e-4 if mode == "fp32" else 5e-2), f"x_hat {mode}: {xerr:.3e}"
+
+
+def test_vae_bs32_bf16_injected_eps_vs_oracle(vae_model, sd_vae):
+    """BASELINE config 1: GenConViT-VAE forward with fixed injected epsilon, bs=32, bf16."""
+    from oracle import nets
+    from oracle.weights import synthetic_eps, synthetic_frames
+    x, eps = synthetic_frames(32, 31), synthetic_eps(32, 32)
+    with torch.no_grad():
+        want = nets.vae_forward(sd_vae, x, eps, resize=False)[0]
+        got = vae_model.set_compute_dtype("bf16")(x.to(DEV), eps=eps.to(DEV))[0].float().cpu()
+    err = (got - want).abs().max().item()
+    assert err <= 2e-2, f"VAE bs32 bf16: {err:.3e}"
+    assert _same_decisions(got, want)
+
+
+def test_vae_kl_side_effect(vae_model, golden):
+    from oracle.weights import synthetic_eps, synthetic_frames
+    g = golden("vae")
+    x = synthetic_frames(g["n"], g["frames_seed"]).to(DEV)
+    eps = synthetic_eps(g["n"], g["eps_seed"]).to(DEV)
+    vae_model.set_compute_dtype("fp32")
+    vae_model.compute_kl = True
+    vae_model._packed = None
+    try:
+        with torch.no_grad():
+            vae_model(x, eps=eps)
+        assert abs(float(vae_model.encoder.kl) - float(g["kl"])) <= 1e-4 * abs(float(g["kl"]))
+    finally:
+        vae_model.compute_kl = False
+        vae_model._packed = None
+
+
+def test_vae_default_eps_is_stochastic_like_the_reference(vae_model):
+    from oracle.weights import synthetic_frames
+    x = synthetic_frames(2, 41).to(DEV)
+    vae_model.set_compute_dtype("bf16")
+    with torch.no_grad():
+        a = vae_model(x)[0]
+        b = vae_model(x)[0]
+    assert not torch.equal(a, b)          # reference draws randn_like even in eval mode (genconvit_vae.py:46)
+
+
+@pytest.fixture(scope="module")
+def full_model(sd_ed, sd_vae, tmp_path_factory):
+    """GenConViT wrapper loaded from weight/*.pth like the reference (raw ED, wrapped VAE)."""
+    import os
+    from model.genconvit import GenConViT
+    d = tmp_path_factory.mktemp("w")
+    os.makedirs(d / "weight")
+    torch.save(sd_ed, d / "weight" / "ed_rand.pth")
+    torch.save({"state_dict": sd_vae, "epoch": 3}, d / "weight" / "vae_rand.pth")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        m = GenConViT(_config(), ed="ed_rand", vae="vae_rand", net="genconvit", fp16=False)
+        with pytest.raises(Exception, match="not found"):
+            GenConViT(_config(), ed="missing", vae="vae_rand", net="ed", fp16=False)
+    finally:
+        os.chdir(cwd)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_full_genconvit_pred_vid_matches_reference_golden(full_model, golden, mode):
+    """The reference's own pred_vid output for a 15-frame video (rows: ED then VAE)."""
+    from model import pred_func
+    from oracle.weights import synthetic_eps, synthetic_frames
+    g = golden("genconvit")
+    x = synthetic_frames(g["n"], g["frames_seed"]).to(DEV)
+    eps = synthetic_eps(g["n"], g["eps_seed"]).to(DEV)
+    full_model.set_compute_dtype(mode)
+    full_model.model_vae.set_epsilon(eps)
+    try:
+        with torch.no_grad():
+            rows = full_model(x).float().cpu()
+        assert rows.shape == (2 * g["n"], 2)
+        err = (rows - g["rows"]).abs().max().item()
+        assert err <= TOL[mode], f"full {mode}: {err:.3e}"
+        assert _same_decisions(rows, g["rows"])
+        cls, val = pred_func.pred_vid(x, full_model)
+        assert cls == g["pred_vid"][0]
+        assert abs(val - g["pred_vid"][1]) <= (1e-4 if mode == "fp32" else 5e-3)
+        assert pred_func.real_or_fake(cls) == g["real_or_fake"]
+    finally:
+        full_model.model_vae.set_epsilon(None)
+
+
+def test_pred_vid_single_frame_and_single_net(ed_model):
+    """N = 1 breaks the reference's .squeeze() (IndexError); the drop-in handles it."""
+    from model import pred_func
+    from oracle.weights import synthetic_frames
+    ed_model.set_compute_dtype("bf16")
+    cls, val = pred_func.pred_vid(synthetic_frames(1, 51).to(DEV), ed_model)
+    assert cls in (0, 1) and 0.0 <= val <= 1.0
+
+
+def test_bs256_fp16_properties(full_model):
+    """BASELINE config 2 size (bs=256, fp16): properties that need no CPU oracle at full size.
+    (a) frames are independent: any sub-batch reproduces its rows; (b) replay is bit-identical;
+    (c) batched per-video scoring equals scoring each 15-frame video on its own."""
+    from model import pred_func
+    from oracle.weights import synthetic_eps, synthetic_frames
+    n, fpv = 255, 15
+    x = synthetic_frames(n, 61).to(DEV)
+    eps = synthetic_eps(n, 62).to(DEV)
+    full_model.set_compute_dtype("fp16")
+    with torch.no_grad():
+        rows = full_model(x, eps=eps).float()
+        again = full_model(x, eps=eps).float()
+        assert torch.equal(rows, again)
+        sub = full_model(x[30:45], eps=eps[30:45]).float()
+        want = torch.cat((rows[30:45], rows[n + 30:n + 45]))
+        assert (sub - want).abs().max().item() <= 2e-2
+        full_model.model_vae.set_epsilon(eps)
+        try:
+            cls, val = pred_func.pred_videos(x, full_model, fpv)
+            full_model.model_vae.set_epsilon(eps[30:45])
+            c1, v1 = pred_func.pred_vid(x[30:45], full_model)
+        finally:
+            full_model.model_vae.set_epsilon(None)
+    assert cls.shape == (n // fpv,)
+    assert int(cls[2]) == c1 and abs(float(val[2]) - v1) <= 5e-3
+
+
+def test_cuda_graph_replay_matches_eager(ed_model):
+    from oracle.weights import synthetic_frames
+    ed_model.set_compute_dtype("bf16")
+    x = synthetic_frames(4, 71).to(DEV)
+    with torch.no_grad():
+        eager = ed_model(x).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ed_model(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = ed_model(x)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, eager)
