@@ -104,6 +104,26 @@ def require_cuda(t: torch.Tensor, what: str):
 # ---- launch counter (bench.py reports how many of our kernels ran in the timed region) ----
 launches = 0
 
+# ---- optional per-launch timing: set ``profile`` to a list and every wrapped launch appends
+# (kernel, work, start_event, end_event); work = FLOPs for GEMMs, algorithmic bytes otherwise ----
+profile = None
+
+
+class _Timed:
+    def __init__(self, kernel, work):
+        self.kernel, self.work = kernel, work
+
+    def __enter__(self):
+        if profile is not None:
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if profile is not None:
+            self.e.record()
+            profile.append((self.kernel, self.work, self.s, self.e))
+        return False
+
 
 def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, gamma=None, residual=None,
          ldr=None, eps=None, eps_c=0, eps_hw=0, mu_out=None, store=STORE_ROWS, ps=(0, 0, 0), out_f32=False,
@@ -124,87 +144,90 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     ep.ps_h, ep.ps_w, ep.ps_co = ps
     ep.ldd = ldd if ldd is not None else N
     ep.out_f32 = 1 if out_f32 else 0
-    rc = load().gcv_gemm(backend, DTYPE_CODE[a.dtype], _p(a), lda if lda is not None else K, _p(b),
-                         ldb if ldb is not None else K, _p(d), M, N, K, C.byref(ep), _stream())
+    lda_, ldb_ = (lda if lda is not None else K), (ldb if ldb is not None else K)
+    tc = backend == GEMM_TCGEN05 or backend >= 1000 or (
+        backend == GEMM_AUTO and a.dtype != torch.float32 and K % 8 == 0 and lda_ % 8 == 0 and ldb_ % 8 == 0
+        and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+    with _Timed("gemm_tcgen05" if tc else "gemm_simt", 2.0 * M * N * K):
+        rc = load().gcv_gemm(backend, DTYPE_CODE[a.dtype], _p(a), lda_, _p(b), ldb_, _p(d), M, N, K, C.byref(ep),
+                             _stream())
     _check(rc, f"gcv_gemm(M={M},N={N},K={K})")
     launches += 1
 
 
 def dwconv7_ln(x, y, taps, bias, ln_w, ln_b, eps, B, H, W, Cc):
     global launches
-    _check(load().gcv_dwconv7_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(taps), _p(bias), _p(ln_w), _p(ln_b), eps,
-                                 B, H, W, Cc, _stream()), "gcv_dwconv7_ln")
+    with _Timed("dwconv7_ln", 2.0 * B * H * W * Cc * x.element_size()):
+        rc = load().gcv_dwconv7_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(taps), _p(bias), _p(ln_w), _p(ln_b), eps,
+                                   B, H, W, Cc, _stream())
+    _check(rc, "gcv_dwconv7_ln")
+    launches += 1
+
+
+def _run(kernel, work, call):
+    """Launch one kernel through the C ABI: count it, optionally time it, raise on a non-zero status."""
+    global launches
+    with _Timed(kernel, work):
+        rc = call()
+    _check(rc, "gcv_" + kernel)
     launches += 1
 
 
 def ln_patchify2(x, a, ln_w, ln_b, eps, B, H, W, Cc):
-    global launches
-    _check(load().gcv_ln_patchify2(DTYPE_CODE[x.dtype], _p(x), _p(a), _p(ln_w), _p(ln_b), eps, B, H, W, Cc, _stream()),
-           "gcv_ln_patchify2")
-    launches += 1
+    es = x.element_size()
+    _run("ln_patchify2", 2.0 * B * H * W * Cc * es, lambda: load().gcv_ln_patchify2(
+        DTYPE_CODE[x.dtype], _p(x), _p(a), _p(ln_w), _p(ln_b), eps, B, H, W, Cc, _stream()))
 
 
 def stem_patchify_nchw(x, a, B, H, W):
-    global launches
     assert x.dtype == torch.float32
-    _check(load().gcv_stem_patchify_nchw(DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()), "gcv_stem_patchify_nchw")
-    launches += 1
+    _run("stem_patchify_nchw", B * H * W * 3.0 * (4 + a.element_size()), lambda: load().gcv_stem_patchify_nchw(
+        DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()))
 
 
 def stem_patchify_nhwc(x, a, B, H, W):
-    global launches
-    _check(load().gcv_stem_patchify_nhwc(DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()), "gcv_stem_patchify_nhwc")
-    launches += 1
+    _run("stem_patchify_nhwc", B * H * W * 3.0 * 2 * a.element_size(), lambda: load().gcv_stem_patchify_nhwc(
+        DTYPE_CODE[a.dtype], _p(x), _p(a), B, H, W, _stream()))
 
 
 def layernorm_rows(x, y, w, b, eps, rows, Cc):
-    global launches
-    _check(load().gcv_layernorm_rows(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, rows, Cc, _stream()),
-           "gcv_layernorm_rows")
-    launches += 1
+    _run("layernorm_rows", 2.0 * rows * Cc * x.element_size(), lambda: load().gcv_layernorm_rows(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, rows, Cc, _stream()))
 
 
 def pool_ln(x, y, w, b, eps, B, HW, Cc):
-    global launches
-    _check(load().gcv_pool_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, B, HW, Cc, _stream()), "gcv_pool_ln")
-    launches += 1
+    _run("pool_ln", 1.0 * B * (HW + 1) * Cc * x.element_size(), lambda: load().gcv_pool_ln(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(b), eps, B, HW, Cc, _stream()))
 
 
 def conv3x3_first(x, y, w, b, stride, act, pool, B, H, W):
-    global launches
     assert x.dtype == torch.float32
-    _check(load().gcv_conv3x3_first(DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(b), stride, act, 1 if pool else 0,
-                                    B, H, W, _stream()), "gcv_conv3x3_first")
-    launches += 1
+    _run("conv3x3_first", B * H * W * 3.0 * 4 + y.numel() * y.element_size(), lambda: load().gcv_conv3x3_first(
+        DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(b), stride, act, 1 if pool else 0, B, H, W, _stream()))
 
 
 def im2col3x3(x, a, B, H, W, Cc, stride):
-    global launches
-    _check(load().gcv_im2col3x3(DTYPE_CODE[x.dtype], _p(x), _p(a), B, H, W, Cc, stride, _stream()), "gcv_im2col3x3")
-    launches += 1
+    es = x.element_size()
+    _run("im2col3x3", (B * H * W * Cc + 9.0 * B * (H // stride) * (W // stride) * Cc) * es, lambda: load().gcv_im2col3x3(
+        DTYPE_CODE[x.dtype], _p(x), _p(a), B, H, W, Cc, stride, _stream()))
 
 
 def maxpool2(x, y, B, H, W, Cc):
-    global launches
-    _check(load().gcv_maxpool2(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_maxpool2")
-    launches += 1
+    _run("maxpool2", 1.25 * B * H * W * Cc * x.element_size(), lambda: load().gcv_maxpool2(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
 
 
 def resize2x_to_nchw(x, y, B, H, W, Cc):
-    global launches
-    _check(load().gcv_resize2x_to_nchw(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_resize2x_to_nchw")
-    launches += 1
+    _run("resize2x_to_nchw", B * H * W * Cc * (x.element_size() + 16.0), lambda: load().gcv_resize2x_to_nchw(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
 
 
 def nhwc_to_nchw_f32(x, y, B, H, W, Cc):
-    global launches
-    _check(load().gcv_nhwc_to_nchw_f32(DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()), "gcv_nhwc_to_nchw_f32")
-    launches += 1
+    _run("nhwc_to_nchw_f32", B * H * W * Cc * (x.element_size() + 4.0), lambda: load().gcv_nhwc_to_nchw_f32(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
 
 
 def score_videos(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out):
-    global launches
     require_cuda(logits, "score_videos")
-    _check(load().gcv_score_videos(_p(logits), n_nets, n_frames, fpv, _p(mean_out), _p(cls_out), _p(val_out), _stream()),
-           "gcv_score_videos")
-    launches += 1
+    _run("score_videos", 8.0 * n_nets * n_frames, lambda: load().gcv_score_videos(
+        _p(logits), n_nets, n_frames, fpv, _p(mean_out), _p(cls_out), _p(val_out), _stream()))

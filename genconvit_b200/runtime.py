@@ -1,0 +1,119 @@
+"""Bulk scoring runtime: pinned-host frames in, per-video (class, score) out.
+
+``VideoScorer`` is the batched, pipelined form of the reference's per-video loop
+(prediction.py:231-266 -> pred_func.pred_vid): every step copies one batch of frames from
+pinned host memory on a copy stream while the previous batch is still computing, replays the
+whole GenConViT forward + fused scoring kernel as ONE CUDA graph, and reads back only the
+per-video results.  Across GPUs the work is sharded by whole batches (frames are independent
+until the per-video mean), weights are replicated, and the only collective is an all-gather of
+the per-video scores (``gather_scores``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine
+from . import lib as L
+
+
+class VideoScorer:
+    def __init__(self, model, batch_frames, frames_per_video, eps=None, use_graph=True, img=224):
+        """model: model.genconvit.GenConViT on a CUDA device; batch_frames: frames per step (whole
+        videos: a multiple of frames_per_video).  eps: None -> fresh N(0,1) noise every step like
+        the reference (genconvit_vae.py:46); or a fixed [batch_frames,12544] tensor."""
+        if batch_frames % frames_per_video:
+            raise ValueError("batch_frames must hold whole videos")
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.n, self.fpv = batch_frames, frames_per_video
+        self.n_videos = batch_frames // frames_per_video
+        self.n_nets = 1 if model.net in ("ed", "vae") else 2
+        dev = self.dev
+        self.x_stage = torch.empty((batch_frames, 3, img, img), dtype=torch.float32, device=dev)
+        self.x_static = torch.empty_like(self.x_stage)
+        self.has_vae = model.net != "ed"
+        self.fixed_eps = eps is not None
+        self.eps = (eps.to(dev, torch.float32).contiguous() if eps is not None
+                    else torch.empty((batch_frames, 12544), dtype=torch.float32, device=dev)) if self.has_vae else None
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_h2d = torch.cuda.Event()
+        self.ev_stage_free = torch.cuda.Event()
+        self.graph = None
+        self.launches_per_step = 0
+        self.out = None                      # [2, V] fp32 on device: row 0 = class, row 1 = score
+        self._prepare(use_graph)
+
+    # -- one step worth of kernels (eager or under capture) --
+    def _step(self):
+        if self.has_vae and not self.fixed_eps:
+            self.eps.normal_()
+        logits = self.model(self.x_static, eps=self.eps).float().contiguous()
+        mean, cls, val = engine.score_videos(logits, self.n_nets, self.n, self.fpv)
+        if self.out is None:
+            self.out = torch.empty((2, self.n_videos), dtype=torch.float32, device=self.dev)
+        self.out[0].copy_(cls)
+        self.out[1].copy_(val)
+
+    def _prepare(self, use_graph):
+        with torch.no_grad():
+            self.x_static.zero_()
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                before = L.launches
+                self._step()                 # warm-up: packs weights, sets kernel attributes
+                self.launches_per_step = L.launches - before
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            if use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step()
+                self.graph = g
+
+    def run_resident(self):
+        """One step on whatever is in ``x_static`` (inputs already in HBM)."""
+        with torch.no_grad():
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._step()
+
+    def submit(self, frames_host, out_host):
+        """Enqueue one batch: pinned-host frames -> device, forward + scoring, results -> pinned host.
+        Asynchronous; overlaps this batch's H2D with the previous batch's compute."""
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_stage_free)
+            self.x_stage.copy_(frames_host, non_blocking=True)
+            self.ev_h2d.record(self.copy_stream)
+        cur.wait_event(self.ev_h2d)
+        self.x_static.copy_(self.x_stage, non_blocking=True)
+        self.ev_stage_free.record(cur)
+        self.run_resident()
+        out_host.copy_(self.out, non_blocking=True)
+
+    def score(self, frames_host):
+        """Synchronous convenience: -> (classes [V] int64, scores [V] float32) on the host."""
+        out = torch.empty((2, self.n_videos), dtype=torch.float32).pin_memory()
+        self.ev_stage_free.record(torch.cuda.current_stream(self.dev))
+        self.submit(frames_host, out)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return out[0].to(torch.int64), out[1].clone()
+
+
+def shard_videos(n_videos: int, rank: int, world: int):
+    """Whole videos per rank, contiguous, remainder spread over the first ranks."""
+    base, rem = divmod(n_videos, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_scores(local: torch.Tensor, group=None) -> torch.Tensor:
+    """The one collective of the path: all-gather of per-video results ([2,V_local] -> [world,2,V_local]).
+    NCCL over NVLink on GPUs (<= 32 KB: latency-bound); gloo in the CPU tests."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out

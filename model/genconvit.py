@@ -38,6 +38,22 @@ class GenConViT(nn.Module):
         if fp16:
             self.half()
 
+    @classmethod
+    def from_modules(cls, model_ed=None, model_vae=None, fp16=False):
+        """Wrap already-constructed sub-networks (no ``weight/*.pth`` round trip); an extension of
+        the reference API used by the benchmark and the tests."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.net = "genconvit" if (model_ed is not None and model_vae is not None) else ("ed" if model_vae is None else "vae")
+        self.fp16 = fp16
+        if model_ed is not None:
+            self.model_ed, self.checkpoint_ed = model_ed.eval(), {}
+        if model_vae is not None:
+            self.model_vae, self.checkpoint_vae = model_vae.eval(), {}
+        if fp16:
+            self.half()
+        return self
+
     def set_compute_dtype(self, dt):
         for m in (getattr(self, "model_ed", None), getattr(self, "model_vae", None)):
             if m is not None:
