@@ -255,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
                 scorer._step()
                 torch.cuda.synchronize(device)
                 prof, lib.profile = lib.profile, None
-        for name, work, s, e in prof:
+        for name, work, s, e, _tag in prof:
             k = kernels.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
             k["launches"] += 1
             k["ms"] += s.elapsed_time(e)

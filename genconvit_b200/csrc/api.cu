@@ -46,6 +46,8 @@ int resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, in
 int nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* mean_out, int32_t* cls_out,
                  float* val_out, cudaStream_t stream);
+int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
+                   int CI, int CO, cudaStream_t stream);
 
 }  // namespace gcv
 
@@ -127,6 +129,10 @@ int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W
 }
 int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream) {
   return nhwc_to_nchw_f32(dtype, x, y, B, H, W, C, S(stream));
+}
+int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
+                       int CI, int CO, void* stream) {
+  return convt2x2_small(dtype, x, y, w, bias, act, B, H, W, CI, CO, S(stream));
 }
 int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video, float* mean_out,
                      int32_t* cls_out, float* val_out, void* stream) {

@@ -192,6 +192,59 @@ nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int B, int H
   y[idx] = to_f<T>(x[((b * H + oy) * (int64_t)W + ox) * C + c]);
 }
 
+// Last decoder layer: ConvTranspose2d(16 -> 3, k2 s2) + activation, NHWC.  K = 16 and N = 12 are far
+// below any tensor-core tile and the layer is pure streaming (32 B in, 24 B out per input pixel), so one
+// thread handles one input pixel: 16 inputs, 4 x 3 dot products, and per output row two RGB pixels
+// (6 x 16-bit = three 32-bit stores; consecutive threads write consecutive 12-byte runs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+convt2x2_16to3_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
+                      const float* __restrict__ bias, int act, int64_t total, int H, int W) {
+  __shared__ float ws[12][16];     // [(i*2+j)*3 + co][ci]
+  __shared__ float bs[3];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) ws[i / 16][i % 16] = w[i];
+  if (threadIdx.x < 3) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wq = (int)(idx % W);
+  const int64_t t = idx / W;
+  const int h = (int)(t % H);
+  const int64_t b = t / H;
+  float in[16];
+  if constexpr (sizeof(T) == 4) {
+    load8<T>(x + idx * 16, in);
+    load8<T>(x + idx * 16 + 8, in + 8);
+  } else {
+    load8<T>(x + idx * 16, in);
+    load8<T>(x + idx * 16 + 8, in + 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float o[6];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int co = 0; co < 3; ++co) {
+        float acc = bs[co];
+        const float* wr = ws[(i * 2 + j) * 3 + co];
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) acc = fmaf(in[ci], wr[ci], acc);
+        o[j * 3 + co] = apply_act(acc, act);
+      }
+    T* dst = y + ((b * (2 * H) + 2 * h + i) * (int64_t)(2 * W) + 2 * wq) * 3;
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) dst[e] = o[e];
+    } else {
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+      d32[0] = pack2<T>(o[0], o[1]);
+      d32[1] = pack2<T>(o[2], o[3]);
+      d32[2] = pack2<T>(o[4], o[5]);
+    }
+  }
+}
+
 // pred_vid / max_prediction_value, batched: one warp per video.
 __global__ void __launch_bounds__(32)
 score_videos_kernel(const float* __restrict__ logits, int n_nets, int n_frames, int fpv, float* __restrict__ mean_out,
@@ -276,6 +329,18 @@ int nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, in
     using T = decltype(tag);
     nhwc_to_nchw_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const T*>(x), y, B, H, W, C);
     return check_launch("nhwc_to_nchw_f32");
+  });
+}
+
+int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
+                   int CI, int CO, cudaStream_t stream) {
+  GCV_REQUIRE(CI == 16 && CO == 3, "convt2x2_small: only the 16 -> 3 output layer is specialised (got %d -> %d)", CI, CO);
+  const int64_t total = (int64_t)B * H * W;
+  return dispatch(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    convt2x2_16to3_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, bias, act, total, H, W);
+    return check_launch("convt2x2_small");
   });
 }
 

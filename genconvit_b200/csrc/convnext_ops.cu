@@ -2,6 +2,8 @@
 // 2x2 patchify, stem patchify, row LayerNorm, global-average-pool + LayerNorm.
 // timm==0.6.5 ConvNeXt as reached from reference model/genconvit_ed.py:68,
 // model/genconvit_vae.py:97 (arithmetic restated in oracle/backbones.py).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gcv {
@@ -126,57 +128,235 @@ dwconv7_ln_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
   }
 }
 
-// ---------------------------------------------------------------------------------
-// Per-row LayerNorm helpers: one warp per row, row cached in registers (C <= 32*MAXV).
-// ---------------------------------------------------------------------------------
-constexpr int LN_MAXV = 48;   // up to C = 1536
-
 template <typename T>
-__device__ __forceinline__ void warp_ln_row(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ w,
-                                            const float* __restrict__ b, float eps, int C, int lane) {
-  float v[LN_MAXV];
-  float s = 0.0f;
+__device__ __forceinline__ float2 ld_pair(const T* p) {
+  if constexpr (sizeof(T) == 4) return __ldg(reinterpret_cast<const float2*>(p));
+  else return unpack2<T>(__ldg(reinterpret_cast<const unsigned int*>(p)));
+}
+
+// ---------------------------------------------------------------------------------
+// Depthwise 7x7 + bias + LayerNorm, column version (the one used for the ConvNeXt-T widths).
+// The kernel is instruction-issue bound on CUDA cores (49 fp32 FMAs per output, no tensor-core
+// form), so everything is arranged to make FMAs the majority of issued instructions:
+//   * thread = (7-row group g, channel pair p) keeps a 7x7-pixel x 2-channel block of fp32
+//     accumulators (98 registers); each of the 13 input rows it needs is loaded ONCE (13 32-bit
+//     channel-pair loads, a warp reads 128 contiguous bytes per pixel) and feeds up to 7 output rows;
+//   * the two channels of a pair are multiplied with one FFMA2 (fma.rn.f32x2): half the issue slots
+//     of scalar FFMA at the same pipe throughput;
+//   * taps live in shared memory ([49][C] fp32, conflict-free 8-byte reads);
+//   * LayerNorm statistics: exact two-pass, half-warp shuffles -> per-half-warp partials in smem ->
+//     fixed-order totals (deterministic, no atomics).
+// One CTA = one 7-pixel-wide column strip of one image (all rows), so no input row is fetched from
+// L2 more than ~13/7 times.  H <= 56 (blockDim = ceil(H/7) * C/2 <= 384).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d.x), "+f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
+template <typename T, int C>
+__global__ void __launch_bounds__(384, 1)
+dwconv7_ln_col_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ taps,
+                      const float* __restrict__ bias, const float* __restrict__ ln_w,
+                      const float* __restrict__ ln_b, float eps, int H, int W, int strips_w) {
+  extern __shared__ __align__(16) float dsm[];
+  float* wsm = dsm;                                       // [49][C]
+  const int n_hw = blockDim.x >> 4;                       // half-warps in the CTA
+  float* part = wsm + 49 * C;                             // [n_hw][49] per-half-warp partial statistics
+  float* tot = part + n_hw * 49;                          // [2][groups][49] mean, rstd
+  constexpr int half_c = C >> 1, hw_per_group = half_c >> 4;
+  const int g = threadIdx.x / half_c, c = 2 * (threadIdx.x - g * half_c);
+  const int groups = blockDim.x / half_c;
+  const int b = blockIdx.x / strips_w, x0 = (blockIdx.x - b * strips_w) * 7;
+  const int hw = threadIdx.x >> 4;
+  const bool reducer = (threadIdx.x & 15) == 0;
+
+  for (int i = threadIdx.x; i < 49 * C / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(taps) + i);
+
+  // 13-bit mask of the input columns x0-3 .. x0+9 that lie inside the image
+  unsigned xmask = 0;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int c = lane + i * 32;
-    v[i] = c < C ? to_f<T>(src[c]) : 0.0f;
-    s += v[i];
+  for (int ix = 0; ix < 13; ++ix) xmask |= (unsigned)(x0 + ix - 3 >= 0 && x0 + ix - 3 < W) << ix;
+
+  const int oy0 = g * 7;
+  // pointer to (row oy0-3, column x0-3, channel c); only dereferenced where the masks allow
+  const T* rowp = x + (((int64_t)b * H + (oy0 - 3)) * W + (x0 - 3)) * C + c;
+  const int64_t row_stride = (int64_t)W * C;
+  const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + c));
+  float2 acc[7][7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[r][i] = bv;
+  const float* wbase = wsm + c;
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int iy = oy0 - 3 + j;
+    if (iy + 1 >= 0 && iy + 1 < H && j < 12) {
+      // pull the next input row into L1 while this row's 343 FFMA2 issue (rows mostly come from L2)
+      const T* nxt = rowp + row_stride;
+#pragma unroll
+      for (int ix = 0; ix < 13; ++ix)
+        if (xmask >> ix & 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + ix * C));
+    }
+    if (iy >= 0 && iy < H) {
+      float2 v[13];
+#pragma unroll
+      for (int ix = 0; ix < 13; ++ix)
+        v[ix] = (xmask >> ix & 1) ? ld_pair<T>(rowp + ix * C) : make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const int dy = j - r;
+        if (dy >= 0 && dy < 7) {
+#pragma unroll
+          for (int dx = 0; dx < 7; ++dx) {
+            const float2 wv = *reinterpret_cast<const float2*>(wbase + (dy * 7 + dx) * C);
+#pragma unroll
+            for (int ox = 0; ox < 7; ++ox) ffma2(acc[r][ox], v[ox + dx], wv);
+          }
+        }
+      }
+    }
+    rowp += row_stride;
   }
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.0f;
+
+  // ---- LayerNorm statistics: mean ----
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) q += (v[i] - mean) * (v[i] - mean);
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      float t = acc[r][i].x + acc[r][i].y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (reducer) part[hw * 49 + r * 7 + i] = t;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 49; i += blockDim.x) {
+    const int gg = i / 49, px = i - gg * 49;
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < hw_per_group; ++k) t += part[(gg * hw_per_group + k) * 49 + px];
+    tot[i] = t * (1.0f / (float)C);
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) dst[c] = from_f<T>((v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float mean = tot[g * 49 + r * 7 + i];
+      acc[r][i].x -= mean; acc[r][i].y -= mean;
+      float t = acc[r][i].x * acc[r][i].x + acc[r][i].y * acc[r][i].y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (reducer) part[hw * 49 + r * 7 + i] = t;       // safe: every read of the mean partials is behind a barrier
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 49; i += blockDim.x) {
+    const int gg = i / 49, px = i - gg * 49;
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < hw_per_group; ++k) t += part[(gg * hw_per_group + k) * 49 + px];
+    tot[groups * 49 + i] = rsqrtf(t * (1.0f / (float)C) + eps);
+  }
+  __syncthreads();
+  const float2 gw = __ldg(reinterpret_cast<const float2*>(ln_w + c));
+  const float2 gb = __ldg(reinterpret_cast<const float2*>(ln_b + c));
+  T* yp = y + (((int64_t)b * H + oy0) * W + x0) * C + c;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    if (oy0 + r < H) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        if (x0 + i < W) {
+          const float rstd = tot[groups * 49 + g * 49 + r * 7 + i];
+          const float o0 = acc[r][i].x * rstd * gw.x + gb.x, o1 = acc[r][i].y * rstd * gw.y + gb.y;
+          T* dst = yp + i * C;
+          if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+          else *reinterpret_cast<uint32_t*>(dst) = pack2<T>(o0, o1);
+        }
+      }
+    }
+    yp += row_stride;
   }
 }
 
-template <typename T>
+// ---------------------------------------------------------------------------------
+// Per-row LayerNorm helpers: a group of LPR lanes (16 or 32) owns one row and keeps it in
+// registers as 8-element (16-byte for 16-bit T) vectors: lane l holds vectors l, l+LPR, ...
+// Two-pass statistics with shuffle reductions inside the group.
+// ---------------------------------------------------------------------------------
+template <typename T, int LPR, int ITER>
+__device__ __forceinline__ void group_ln_row(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ w,
+                                             const float* __restrict__ b, float eps, int C, int gl) {
+  float v[ITER][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+      load8<T>(src + c, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += (v[i][e] - mean) * (v[i][e] - mean);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+      float g[8], be[8];
+      load8<float>(w + c, g);
+      load8<float>(b + c, be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = (v[i][e] - mean) * rstd * g[e] + be[e];
+      store8<T>(dst + c, v[i]);
+    }
+  }
+}
+
+template <typename T, int LPR, int ITER>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
                       const float* __restrict__ b, float eps, int64_t rows, int C) {
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  warp_ln_row<T>(x + row * C, y + row * C, w, b, eps, C, threadIdx.x & 31);
+  constexpr int RPB = 256 / LPR;
+  int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
+  // inactive groups clamp to the last row (they recompute it) so the group shuffles stay full-warp converged
+  if (row >= rows) row = rows - 1;
+  group_ln_row<T, LPR, ITER>(x + row * C, y + row * C, w, b, eps, C, threadIdx.x % LPR);
 }
 
 // LayerNorm2d over C of every pixel, written straight into the im2col matrix of the
 // following 2x2 stride-2 conv: pixel (2ho+kh, 2wo+kw) -> row (b,ho,wo), columns
 // [(kh*2+kw)*C, +C).  Pixels of an odd last row/column are dropped (floor semantics).
-template <typename T>
+template <typename T, int LPR, int ITER>
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const T* __restrict__ x, T* __restrict__ a, const float* __restrict__ w,
                     const float* __restrict__ b, float eps, int B, int H, int W, int C) {
+  constexpr int RPB = 256 / LPR;
   const int Ho = H / 2, Wo = W / 2;
-  const int64_t idx = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  int64_t idx = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
   const int64_t total = (int64_t)B * Ho * 2 * Wo * 2;
-  if (idx >= total) return;
+  if (idx >= total) idx = total - 1;
   const int wi = (int)(idx % (2 * Wo));
   const int64_t t = idx / (2 * Wo);
   const int hi = (int)(t % (2 * Ho));
@@ -184,7 +364,20 @@ ln_patchify2_kernel(const T* __restrict__ x, T* __restrict__ a, const float* __r
   const T* src = x + ((bi * H + hi) * W + wi) * C;
   const int64_t row = (bi * Ho + (hi >> 1)) * Wo + (wi >> 1);
   T* dst = a + row * (4 * (int64_t)C) + ((hi & 1) * 2 + (wi & 1)) * C;
-  warp_ln_row<T>(src, dst, w, b, eps, C, threadIdx.x & 31);
+  group_ln_row<T, LPR, ITER>(src, dst, w, b, eps, C, threadIdx.x % LPR);
+}
+
+// pick (lanes per row, vectors per lane) for a channel count; C % 8 == 0, C <= 2048
+template <typename F>
+int ln_dispatch(int C, F&& f) {
+  const int vecs = C / 8;
+  if (vecs <= 16) return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
+  if (vecs <= 32) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
+  if (vecs <= 64) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 2>{});
+  if (vecs <= 96) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 3>{});
+  if (vecs <= 128) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 4>{});
+  if (vecs <= 192) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 6>{});
+  return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 8>{});
 }
 
 // Stem im2col (4x4 stride 4, 3 channels): row (b,ho,wo), column (kh*4+kw)*3 + c.
@@ -291,6 +484,34 @@ int dispatch(int dtype, F&& f) {
 int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
                const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream) {
   GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
+  const int groups = (H + 6) / 7;
+  if ((C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384) {
+    const int strips_w = (W + 6) / 7;
+    const int64_t grid = (int64_t)B * strips_w;
+    GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
+    const int threads = groups * (C / 2);
+    const size_t smem = (size_t)(49 * C + (threads / 16) * 49 + 2 * groups * 49) * sizeof(float);
+    return dispatch(dtype, [&](auto tag) -> int {
+      using T = decltype(tag);
+      auto launch = [&](auto cc) -> int {
+        constexpr int CC = decltype(cc)::value;
+        static bool attr_done = false;
+        if (!attr_done) {
+          cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          attr_done = true;
+        }
+        dwconv7_ln_col_kernel<T, CC><<<(unsigned)grid, threads, smem, stream>>>(
+            reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w);
+        return check_launch("dwconv7_ln");
+      };
+      switch (C) {
+        case 96: return launch(std::integral_constant<int, 96>{});
+        case 192: return launch(std::integral_constant<int, 192>{});
+        case 384: return launch(std::integral_constant<int, 384>{});
+        default: return launch(std::integral_constant<int, 768>{});
+      }
+    });
+  }
   const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
   const int64_t grid = (int64_t)B * tiles_w * tiles_h;
   GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
@@ -311,13 +532,16 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
 
 int ln_patchify2(int dtype, const void* x, void* a, const float* w, const float* b, float eps, int B, int H, int W, int C,
                  cudaStream_t stream) {
-  GCV_REQUIRE(C <= 32 * LN_MAXV && H >= 2 && W >= 2, "ln_patchify2: unsupported C=%d H=%d W=%d", C, H, W);
+  GCV_REQUIRE(C % 8 == 0 && C <= 2048 && H >= 2 && W >= 2, "ln_patchify2: unsupported C=%d H=%d W=%d", C, H, W);
   const int64_t total = (int64_t)B * (H / 2) * 2 * (W / 2) * 2;
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
-    ln_patchify2_kernel<T><<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(
-        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(a), w, b, eps, B, H, W, C);
-    return check_launch("ln_patchify2");
+    return ln_dispatch(C, [&](auto lpr, auto iter) -> int {
+      constexpr int LPR = decltype(lpr)::value, ITER = decltype(iter)::value, RPB = 256 / LPR;
+      ln_patchify2_kernel<T, LPR, ITER><<<(unsigned)((total + RPB - 1) / RPB), 256, 0, stream>>>(
+          reinterpret_cast<const T*>(x), reinterpret_cast<T*>(a), w, b, eps, B, H, W, C);
+      return check_launch("ln_patchify2");
+    });
   });
 }
 
@@ -337,12 +561,15 @@ int stem_patchify(int dtype, bool nchw, const void* x, void* a, int B, int H, in
 
 int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
                    cudaStream_t stream) {
-  GCV_REQUIRE(C <= 32 * LN_MAXV && rows > 0, "layernorm_rows: unsupported C=%d", C);
+  GCV_REQUIRE(C % 8 == 0 && C <= 2048 && rows > 0, "layernorm_rows: unsupported C=%d", C);
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
-    layernorm_rows_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(
-        reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, b, eps, rows, C);
-    return check_launch("layernorm_rows");
+    return ln_dispatch(C, [&](auto lpr, auto iter) -> int {
+      constexpr int LPR = decltype(lpr)::value, ITER = decltype(iter)::value, RPB = 256 / LPR;
+      layernorm_rows_kernel<T, LPR, ITER><<<(unsigned)((rows + RPB - 1) / RPB), 256, 0, stream>>>(
+          reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, b, eps, rows, C);
+      return check_launch("layernorm_rows");
+    });
   });
 }
 

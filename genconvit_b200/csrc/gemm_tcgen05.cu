@@ -25,12 +25,15 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                       // 64 x 16-bit = one 128-byte swizzle row
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: TLP hides tcgen05.ld / MUFU / smem latency
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
-constexpr int kTileSmem = 192 * 1024;
+constexpr int kTileSmem = 185 * 1024;            // 227 KB budget minus control block, epilogue staging, alignment slack
 constexpr int kCtrlSmem = 1024;
-constexpr int kDynSmem = kCtrlSmem + 1024 + kTileSmem;   // +1024 alignment slack
+constexpr int kStageRow = 80;                            // staged row: 32 x 16-bit + 16 B pad (conflict-free v4 access)
+constexpr int kStageWarp = 32 * kStageRow;               // per epilogue warp: 32 rows x 32 columns
+constexpr int kStageSmem = kEpiWarps * kStageWarp;
+constexpr int kDynSmem = kCtrlSmem + kStageSmem + 1024 + kTileSmem;   // +1024 alignment slack
 constexpr uint32_t kTmemCols = 512;
 
 struct Params {
@@ -122,44 +125,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return d;
 }
 
-// ---- vectorised epilogue: 8 consecutive columns of one row ---------------------
+// Cold path, kept out of line so the hot epilogue loop stays small in the instruction cache: element-wise
+// epilogue for 8 consecutive columns (ragged right edge, fp32 / unaligned outputs, VAE reparameterisation).
 template <typename T>
-__device__ __forceinline__ void epilogue_vec8(const gcv_epilogue& ep, int64_t m, int n, float* v, void* D) {
-  if (ep.bias) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (ep.act != GCV_ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-  }
-  if (ep.gamma) {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
-    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-  }
-  if (ep.residual) {
-    float r[8];
-    load8<T>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + n, r);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += r[j];
-  }
-  int64_t off;
-  if (ep.store == GCV_STORE_PIXEL_SHUFFLE2) {
-    const int ij = n / ep.ps_co, co = n - ij * ep.ps_co;
-    const int64_t hw = (int64_t)ep.ps_h * ep.ps_w;
-    const int64_t b = m / hw;
-    const int r = (int)(m - b * hw);
-    const int h = r / ep.ps_w, w = r - h * ep.ps_w;
-    off = ((b * (2 * ep.ps_h) + 2 * h + (ij >> 1)) * (int64_t)(2 * ep.ps_w) + 2 * w + (ij & 1)) * ep.ps_co + co;
-  } else {
-    off = m * ep.ldd + n;
-  }
-  if (ep.out_f32) store8<float>(reinterpret_cast<float*>(D) + off, v);
-  else store8<T>(reinterpret_cast<T*>(D) + off, v);
+__device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, int n, int N, float v0, float v1,
+                                            float v2, float v3, float v4, float v5, float v6, float v7, void* D) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+#pragma unroll 1
+  for (int e = 0; e < 8; ++e)
+    if (n + e < N) epilogue_one<T>(ep, m, n + e, N, v[e], D);
 }
 
 template <typename T>
@@ -173,7 +147,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + 1023u) & ~1023u;
+  uint8_t* stage_base = smem_raw + kCtrlSmem;            // epilogue staging, kStageWarp bytes per warp
+  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.block_n * BK * 2;
@@ -251,43 +226,121 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue =====================
+    // Phase A (thread = accumulator row): tcgen05.ld 32 columns, bias / activation / layer-scale /
+    // residual in registers, 16-bit result parked in this warp's smem staging tile.
+    // Phase B (lane = 16-byte piece): the 32x32 staged tile leaves as 8 rows x 64 contiguous bytes per
+    // store instruction -- full 32-byte sectors instead of 32 scattered 16-byte row fragments.
     const int ew = warp - 2;
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                            // the two warps of a quarter split the column chunks
+    const int sub = ew >> 2;                             // the 4 warps of a quarter take chunks sub, sub+4, ...
     const int chunks = p.block_n / 32;
     const bool vec_ok = p.vec_ok != 0;
+    uint8_t* my_stage = stage_base + ew * kStageWarp;
+    const gcv_epilogue& ep = p.ep;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int as = it & 1;
       mbar_wait(smem_u32(tmem_full + as), (it >> 1) & 1);
       tc_fence_after();
-      const int64_t m = (int64_t)m_blk * BM + quarter * 32 + lane;
+      const int64_t m_warp = (int64_t)m_blk * BM + quarter * 32;
+      const int64_t m = m_warp + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
-      for (int c = half; c < chunks; c += 2) {
-        uint32_t r[32];
-        tc_ld32(t_row + c * 32, r);
-        tc_wait_ld();
+      if (sub >= chunks) {                               // narrow tile: this warp has no chunk, release immediately
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+      }
+      for (int c = sub; c < chunks; c += 4) {
+        float v[32];
+        {
+          uint32_t r[32];
+          tc_ld32(t_row + c * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        }
+        if (c + 4 >= chunks) {
+          tc_fence_before();                             // all TMEM reads of this tile by this warp are done:
+          __syncwarp();                                  // hand the accumulator stage back to the MMA warp early
+          if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+        }
         const int n0 = n_blk * p.block_n + c * 32;
-        if (m < p.M) {
+        if (!vec_ok) {
+          if (m < p.M) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n = n0 + j * 8;
-            float v[8];
+            for (int j = 0; j < 4; ++j)
+              epilogue_slow8<T>(ep, m, n0 + j * 8, p.N, v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3],
+                                v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7], D);
+          }
+          continue;
+        }
+        // ---- phase A ----
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j * 8 + e]);
-            if (vec_ok && n + 8 <= p.N) {
-              epilogue_vec8<T>(p.ep, m, n, v, D);
-            } else {
-              for (int e = 0; e < 8; ++e)
-                if (n + e < p.N) epilogue_one<T>(p.ep, m, n + e, p.N, v[e], D);
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + j * 8;
+          float* w = v + j * 8;
+          if (n + 8 <= p.N) {
+            if (ep.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+              w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+              w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+            }
+            if (ep.act != GCV_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] = apply_act_fast(w[e], ep.act);
+            }
+            if (ep.gamma) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+              w[0] *= g0.x; w[1] *= g0.y; w[2] *= g0.z; w[3] *= g0.w;
+              w[4] *= g1.x; w[5] *= g1.y; w[6] *= g1.z; w[7] *= g1.w;
+            }
+            if (ep.residual && m < p.M) {
+              float rr[8];
+              load8<T>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + n, rr);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] += rr[e];
+            }
+          } else {
+            // ragged right edge (N % 8 != 0): finish these columns element-wise, nothing staged
+            if (m < p.M && n < p.N)
+              epilogue_slow8<T>(ep, m, n, p.N, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], D);
+          }
+          uint4 q;
+          q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
+          q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
+          *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
+        }
+        __syncwarp();
+        // ---- phase B ----
+        const int piece = lane & 3;
+        const int n = n0 + piece * 8;
+        if (n + 8 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2);
+            const int64_t mm = m_warp + row;
+            if (mm < p.M) {
+              const uint4 q = *reinterpret_cast<const uint4*>(my_stage + row * kStageRow + piece * 16);
+              int64_t off;
+              if (ep.store == GCV_STORE_PIXEL_SHUFFLE2) {
+                const int ij = n / ep.ps_co, co = n - ij * ep.ps_co;
+                const int64_t hw = (int64_t)ep.ps_h * ep.ps_w;
+                const int64_t b = mm / hw;
+                const int rem = (int)(mm - b * hw);
+                const int h = rem / ep.ps_w, wq = rem - h * ep.ps_w;
+                off = ((b * (2 * ep.ps_h) + 2 * h + (ij >> 1)) * (int64_t)(2 * ep.ps_w) + 2 * wq + (ij & 1)) * ep.ps_co + co;
+              } else {
+                off = mm * ep.ldd + n;
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(D) + off) = q;
             }
           }
         }
+        __syncwarp();                                    // staging tile is reused by the next chunk
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
     }
   }
 
@@ -392,7 +445,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   {
     const size_t es = ep->out_f32 ? 4 : 2;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    bool ok = ep->eps == nullptr && al16(D) && (!ep->bias || al16(ep->bias)) && (!ep->gamma || al16(ep->gamma));
+    bool ok = ep->eps == nullptr && !ep->out_f32 && al16(D) && (!ep->bias || al16(ep->bias)) && (!ep->gamma || al16(ep->gamma));
     if (ep->store == GCV_STORE_ROWS) ok = ok && (ep->ldd * es) % 16 == 0;
     else ok = ok && ep->ps_co % 8 == 0;
     if (ep->residual) ok = ok && al16(ep->residual) && ep->ldr % 8 == 0;

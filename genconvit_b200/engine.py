@@ -137,8 +137,11 @@ def _pack_conv3x3(w, dev, dt):
 
 
 def _pack_convt(w, b, dev, dt):
-    """ConvTranspose2d k2 s2 weight [Ci,Co,2,2] -> GEMM B [(i,j,co), Ci] and the bias repeated per tap."""
+    """ConvTranspose2d k2 s2 weight [Ci,Co,2,2] -> GEMM B [(i,j,co), Ci] and the bias repeated per tap.
+    The 16 -> 3 output layer runs on the streaming kernel, which takes fp32 weights."""
     co = w.shape[1]
+    if (w.shape[0], co) == (16, 3):
+        dt = torch.float32
     return _cd(w.permute(2, 3, 1, 0).reshape(4 * co, w.shape[0]), dev, dt), _f32(b.repeat(4), dev)
 
 
@@ -147,8 +150,11 @@ def _run_convt_stack(x, layers, b, h, w, act, dt, dev, backend):
     for wt, bias in layers:
         co, ci = wt.shape[0] // 4, wt.shape[1]
         out = _empty((b * 4 * h * w, co), dt, dev)
-        L.gemm(x, wt, out, b * h * w, 4 * co, ci, bias=bias, act=act, store=L.STORE_PIXEL_SHUFFLE2, ps=(h, w, co),
-               backend=backend)
+        if (ci, co) == (16, 3):
+            L.convt2x2_small(x, out, wt, bias, act, b, h, w, ci, co)
+        else:
+            L.gemm(x, wt, out, b * h * w, 4 * co, ci, bias=bias, act=act, store=L.STORE_PIXEL_SHUFFLE2,
+                   ps=(h, w, co), backend=backend)
         x, h, w = out, 2 * h, 2 * w
     return x, h, w
 

@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_dwconv7_ln", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     lib.gcv_conv3x3_first.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_im2col3x3.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_score_videos.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
@@ -110,8 +111,8 @@ profile = None
 
 
 class _Timed:
-    def __init__(self, kernel, work):
-        self.kernel, self.work = kernel, work
+    def __init__(self, kernel, work, tag=""):
+        self.kernel, self.work, self.tag = kernel, work, tag
 
     def __enter__(self):
         if profile is not None:
@@ -121,7 +122,7 @@ class _Timed:
     def __exit__(self, *exc):
         if profile is not None:
             self.e.record()
-            profile.append((self.kernel, self.work, self.s, self.e))
+            profile.append((self.kernel, self.work, self.s, self.e, self.tag))
         return False
 
 
@@ -148,7 +149,9 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     tc = backend == GEMM_TCGEN05 or backend >= 1000 or (
         backend == GEMM_AUTO and a.dtype != torch.float32 and K % 8 == 0 and lda_ % 8 == 0 and ldb_ % 8 == 0
         and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
-    with _Timed("gemm_tcgen05" if tc else "gemm_simt", 2.0 * M * N * K):
+    tag = f"M{M} N{N} K{K} act{act}" + ("+res" if residual is not None else "") + ("+eps" if eps is not None else "") + \
+        ("+ps" if store else "")
+    with _Timed("gemm_tcgen05" if tc else "gemm_simt", 2.0 * M * N * K, tag):
         rc = load().gcv_gemm(backend, DTYPE_CODE[a.dtype], _p(a), lda_, _p(b), ldb_, _p(d), M, N, K, C.byref(ep),
                              _stream())
     _check(rc, f"gcv_gemm(M={M},N={N},K={K})")
@@ -157,17 +160,17 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
 
 def dwconv7_ln(x, y, taps, bias, ln_w, ln_b, eps, B, H, W, Cc):
     global launches
-    with _Timed("dwconv7_ln", 2.0 * B * H * W * Cc * x.element_size()):
+    with _Timed("dwconv7_ln", 2.0 * B * H * W * Cc * x.element_size(), f"B{B} H{H} W{W} C{Cc}"):
         rc = load().gcv_dwconv7_ln(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(taps), _p(bias), _p(ln_w), _p(ln_b), eps,
                                    B, H, W, Cc, _stream())
     _check(rc, "gcv_dwconv7_ln")
     launches += 1
 
 
-def _run(kernel, work, call):
+def _run(kernel, work, call, tag=""):
     """Launch one kernel through the C ABI: count it, optionally time it, raise on a non-zero status."""
     global launches
-    with _Timed(kernel, work):
+    with _Timed(kernel, work, tag):
         rc = call()
     _check(rc, "gcv_" + kernel)
     launches += 1
@@ -215,6 +218,11 @@ def im2col3x3(x, a, B, H, W, Cc, stride):
 def maxpool2(x, y, B, H, W, Cc):
     _run("maxpool2", 1.25 * B * H * W * Cc * x.element_size(), lambda: load().gcv_maxpool2(
         DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
+
+
+def convt2x2_small(x, y, w, bias, act, B, H, W, ci, co):
+    _run("convt2x2_small", B * H * W * (ci + 4.0 * co) * x.element_size(), lambda: load().gcv_convt2x2_small(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), act, B, H, W, ci, co, _stream()))
 
 
 def resize2x_to_nchw(x, y, B, H, W, Cc):

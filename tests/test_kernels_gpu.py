@@ -113,10 +113,30 @@ def test_gemm_pixel_shuffle_is_conv_transpose(cfg, dtype):
     w, bias = _rand(ci, co, 2, 2, seed=2, scale=ci ** -0.5), _rand(co, seed=3)
     want = F.leaky_relu(F.conv_transpose2d(x, w, bias, stride=2), 0.01).permute(0, 2, 3, 1)
     wp, bp = _pack_convt(w, bias, DEV, dtype)
+    wp = wp.to(dtype)
     tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, ci).to(dtype).contiguous()
     out = torch.empty((B, 2 * H, 2 * W, co), device=DEV, dtype=dtype)
     L.gemm(tokens, wp, out, B * H * W, 4 * co, ci, bias=bp, act=L.ACT_LEAKY, store=L.STORE_PIXEL_SHUFFLE2, ps=(H, W, co))
     _close(out, want, TOL[dtype], f"convT {cfg}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("act", ["relu", "leaky"])
+def test_convt2x2_small_output_layer(dtype, act):
+    """The decoders' 16 -> 3 output layer on the streaming kernel (genconvit_ed.py:56-57, genconvit_vae.py:77-78)."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_convt
+    B, H, W = 3, 9, 21
+    x = _rand(B, 16, H, W, seed=1)
+    w, bias = _rand(16, 3, 2, 2, seed=2, scale=0.25), _rand(3, seed=3)
+    y = F.conv_transpose2d(x, w, bias, stride=2)
+    want = (F.relu(y) if act == "relu" else F.leaky_relu(y, 0.01)).permute(0, 2, 3, 1)
+    wp, bp = _pack_convt(w, bias, DEV, dtype)
+    assert wp.dtype == torch.float32
+    tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, 16).to(dtype).contiguous()
+    out = torch.full((B, 2 * H, 2 * W, 3), float("nan"), device=DEV, dtype=dtype)
+    L.convt2x2_small(tokens, out, wp, bp, L.ACT_RELU if act == "relu" else L.ACT_LEAKY, B, H, W, 16, 3)
+    _close(out, want, TOL[dtype], "convt2x2_small")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -140,7 +160,7 @@ def test_gemm_reparam_epilogue(dtype):
 # --------------------------------------------------------------------------- ConvNeXt kernels
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("cfg", [(2, 56, 56, 96), (1, 28, 28, 192), (2, 14, 14, 384), (2, 7, 7, 768), (1, 3, 3, 768),
-                                 (1, 9, 13, 96)])
+                                 (1, 9, 13, 96), (3, 28, 28, 96), (2, 5, 20, 192), (1, 9, 13, 64), (2, 8, 8, 160)])
 def test_dwconv7_ln(cfg, dtype):
     L = _lib()
     B, H, W, C = cfg
