@@ -28,12 +28,14 @@ constexpr int BK = 64;                       // 64 x 16-bit = one 128-byte swizz
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: TLP hides tcgen05.ld / MUFU / smem latency
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
-constexpr int kTileSmem = 185 * 1024;            // 227 KB budget minus control block, epilogue staging, alignment slack
+constexpr int kTileSmem = 160 * 1024;            // 227 KB budget minus control block, epilogue staging, vectors, slack
+constexpr int kVecMaxN = 3072;                   // bias / layer-scale vectors up to this N are staged in smem
+constexpr int kVecSmem = 2 * kVecMaxN * 4;
 constexpr int kCtrlSmem = 1024;
 constexpr int kStageRow = 80;                            // staged row: 32 x 16-bit + 16 B pad (conflict-free v4 access)
 constexpr int kStageWarp = 32 * kStageRow;               // per epilogue warp: 32 rows x 32 columns
 constexpr int kStageSmem = kEpiWarps * kStageWarp;
-constexpr int kDynSmem = kCtrlSmem + kStageSmem + 1024 + kTileSmem;   // +1024 alignment slack
+constexpr int kDynSmem = kCtrlSmem + kStageSmem + kVecSmem + 1024 + kTileSmem;   // +1024 alignment slack
 constexpr uint32_t kTmemCols = 512;
 
 struct Params {
@@ -43,6 +45,7 @@ struct Params {
   int tiles_m, tiles_n;
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
+  int vec_smem;        // bias / gamma are staged in shared memory (N <= kVecMaxN)
   gcv_epilogue ep;
 };
 
@@ -148,7 +151,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint8_t* stage_base = smem_raw + kCtrlSmem;            // epilogue staging, kStageWarp bytes per warp
-  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + 1023u) & ~1023u;
+  float* vec_bias = reinterpret_cast<float*>(smem_raw + kCtrlSmem + kStageSmem);   // [kVecMaxN] bias, then gamma
+  float* vec_gamma = vec_bias + kVecMaxN;
+  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.block_n * BK * 2;
@@ -172,6 +177,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                  "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.vec_smem) {
+    // bias / layer-scale vectors are read by every epilogue thread for every tile: keep them on chip
+    for (int i = threadIdx.x; i < p.N; i += kThreads) {
+      vec_bias[i] = p.ep.bias ? __ldg(p.ep.bias + i) : 0.0f;
+      vec_gamma[i] = p.ep.gamma ? __ldg(p.ep.gamma + i) : 1.0f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -281,7 +293,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int n = n0 + j * 8;
           float* w = v + j * 8;
           if (n + 8 <= p.N) {
-            if (ep.bias) {
+            if (p.vec_smem) {
+              if (ep.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
+                w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+                w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+              }
+            } else if (ep.bias) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
               w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
@@ -292,8 +311,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int e = 0; e < 8; ++e) w[e] = apply_act_fast(w[e], ep.act);
             }
             if (ep.gamma) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+              const float4 g0 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n)
+                                           : __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+              const float4 g1 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n + 4)
+                                           : __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
               w[0] *= g0.x; w[1] *= g0.y; w[2] *= g0.z; w[3] *= g0.w;
               w[4] *= g1.x; w[5] *= g1.y; w[6] *= g1.z; w[7] *= g1.w;
             }
@@ -393,7 +414,8 @@ int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_
 
 int pick_block_n(int64_t M, int N, int sms) {
   // Largest tile that still gives every SM work; N tiles must be multiples of 32 (epilogue chunk) <= 256.
-  const int cands[] = {256, 192, 128, 96, 64, 32};
+  // 256 and 128 give every epilogue warp the same number of 32-column chunks (4 warps per lane quarter)
+  const int cands[] = {256, 128, 192, 96, 64, 32};
   const int64_t tiles_m = (M + BM - 1) / BM;
   int best = 32;
   for (int c : cands) {
@@ -450,6 +472,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
     else ok = ok && ep->ps_co % 8 == 0;
     if (ep->residual) ok = ok && al16(ep->residual) && ep->ldr % 8 == 0;
     p.vec_ok = ok ? 1 : 0;
+    p.vec_smem = (ok && N <= kVecMaxN && (ep->bias || ep->gamma)) ? 1 : 0;
   }
 
   CUtensorMap ma, mb;
