@@ -114,6 +114,7 @@ def gather_scores(local: torch.Tensor, group=None) -> torch.Tensor:
     NCCL over NVLink on GPUs (<= 32 KB: latency-bound); gloo in the CPU tests."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-    return out
+    local = local.contiguous()
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out.view((world,) + tuple(local.shape))
