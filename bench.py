@@ -39,6 +39,18 @@ GFLOP_PER_FRAME_CONTRACTION = 29.49      # BASELINE.md section 2 (2xMAC, mu once
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is not None:
+        os.write(_RESULT_FD, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -169,7 +181,7 @@ def run_reference(args, rank, world):
                                    f"{threads} threads; oracle port of the reference forward (timm not installable)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -311,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -334,6 +346,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: route everything libraries print (e.g. NCCL's version banner)
+    # to stderr and keep the real stdout for the result.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
