@@ -48,6 +48,9 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
                  float* val_out, cudaStream_t stream);
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
+bool mlp_fused_supported(int dtype, int C);
+int mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+              const float* gamma, void* x, int64_t M, int C, cudaStream_t stream);
 
 }  // namespace gcv
 
@@ -90,6 +93,12 @@ int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, 
   if (backend == GCV_GEMM_SIMT) return gemm_simt(dtype, A, lda, B, ldb, D, M, N, K, ep, S(stream));
   set_error("gcv_gemm: unknown backend %d", backend);
   return GCV_ERR_BAD_ARG;
+}
+
+int gcv_mlp_fused_supported(int dtype, int C) { return mlp_fused_supported(dtype, C) ? 1 : 0; }
+int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                  const float* gamma, void* x, int64_t M, int C, void* stream) {
+  return mlp_fused(dtype, y, w1, b1, w2, b2, gamma, x, M, C, S(stream));
 }
 
 int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,

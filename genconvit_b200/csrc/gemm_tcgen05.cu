@@ -16,8 +16,10 @@
 //               VAE reparameterisation, 16-byte stores (rows or convT pixel shuffle)
 // The two TMEM stages let tile i's epilogue overlap tile i+1's MMAs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace gcv {
 
@@ -28,6 +30,7 @@ constexpr int BK = 64;                       // 64 x 16-bit = one 128-byte swizz
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: TLP hides tcgen05.ld / MUFU / smem latency
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccStages = 8;              // TMEM accumulator ring: 512 columns / block_n
 constexpr int kTileSmem = 160 * 1024;            // 227 KB budget minus control block, epilogue staging, vectors, slack
 constexpr int kVecMaxN = 3072;                   // bias / layer-scale vectors up to this N are staged in smem
 constexpr int kVecSmem = 2 * kVecMaxN * 4;
@@ -41,81 +44,14 @@ constexpr uint32_t kTmemCols = 512;
 struct Params {
   int64_t M;
   int N, K;
-  int block_n, num_stages;
+  int block_n, num_stages, acc_stages;
   int tiles_m, tiles_n;
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
   int vec_smem;        // bias / gamma are staged in shared memory (N <= kVecMaxN)
+  int debug;           // profiling knob (GCV_DEBUG): 1 = epilogue skips all work, 2 = skips stores
   gcv_epilogue ep;
 };
-
-// ---- PTX wrappers ------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFu) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) __trap();      // ~2 s at 2 GHz
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows are 128 B, 8-row atoms are 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), SWIZZLE_128B=2 [61,64))
@@ -148,8 +84,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + kMaxAccStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kMaxAccStages);
   uint8_t* stage_base = smem_raw + kCtrlSmem;            // epilogue staging, kStageWarp bytes per warp
   float* vec_bias = reinterpret_cast<float*>(smem_raw + kCtrlSmem + kStageSmem);   // [kVecMaxN] bias, then gamma
   float* vec_gamma = vec_bias + kVecMaxN;
@@ -166,7 +102,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(smem_u32(full_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.acc_stages; ++s) {
       mbar_init(smem_u32(tmem_full + s), 1);
       mbar_init(smem_u32(tmem_empty + s), kEpiWarps);
     }
@@ -213,10 +149,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(smem_u32(tmem_empty + as), ((it >> 1) & 1) ^ 1);
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tmem_empty + as), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -234,6 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(smem_u32(tmem_full + as));             // accumulator complete
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
@@ -249,11 +186,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool vec_ok = p.vec_ok != 0;
     uint8_t* my_stage = stage_base + ew * kStageWarp;
     const gcv_epilogue& ep = p.ep;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int as = -1;
+    uint32_t aphase = 1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
-      const int as = it & 1;
-      mbar_wait(smem_u32(tmem_full + as), (it >> 1) & 1);
+      if (++as == p.acc_stages) as = 0;
+      if (as == 0) aphase ^= 1;
+      mbar_wait(smem_u32(tmem_full + as), aphase);
       tc_fence_after();
       const int64_t m_warp = (int64_t)m_blk * BM + quarter * 32;
       const int64_t m = m_warp + lane;
@@ -262,6 +201,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+      }
+      if (p.debug == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && sub < chunks) mbar_arrive(smem_u32(tmem_empty + as));
+        continue;
       }
       for (int c = sub; c < chunks; c += 4) {
         float v[32];
@@ -335,6 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
         }
         __syncwarp();
+        if (p.debug == 2) { __syncwarp(); continue; }
         // ---- phase B ----
         const int piece = lane & 3;
         const int n = n0 + piece * 8;
@@ -456,6 +402,8 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, (int)N, sms);
   GCV_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "block_n must be a multiple of 32 in [32,256]");
   const int stage_bytes = BM * BK * 2 + p.block_n * BK * 2;
+  p.acc_stages = 512 / p.block_n;
+  if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
   p.num_stages = kTileSmem / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   p.tiles_m = (int)((M + BM - 1) / BM);
@@ -464,6 +412,11 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   // cute::UMMA::InstrDescriptor: c_format F32 [4,6), a/b format [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   p.ep = *ep;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GCV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   {
     const size_t es = ep->out_f32 ? 4 : 2;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

@@ -12,12 +12,16 @@ CPU oracle (``oracle/``), which is never imported from here.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import lib as L
 
 DEPTHS = (3, 3, 9, 3)
 DIMS = (96, 192, 384, 768)
+# the fused fc1->GELU->fc2 kernel (stages 0-1); GCV_NO_FUSED_MLP=1 falls back to two GEMM launches (A/B timing)
+FUSED_MLP = os.environ.get("GCV_NO_FUSED_MLP", "0") != "1"
 
 
 def _f32(t, dev):
@@ -100,15 +104,19 @@ class PackedConvNeXt:
                 L.gemm(a, st["ds_w"], x, m2, c, 4 * cin, bias=st["ds_b"], backend=backend)
                 segs, m = new, m2
             y = _empty((m, c), dt, dev)
-            hid = _empty((m, 4 * c), dt, dev)
+            fused = FUSED_MLP and backend == L.GEMM_AUTO and L.mlp_fused_supported(dt, c)
+            hid = None if fused else _empty((m, 4 * c), dt, dev)
             for blk in st["blocks"]:
                 r = 0
                 for b, h, w in segs:
                     L.dwconv7_ln(x[r:], y[r:], blk["taps"], blk["dw_b"], blk["ln_w"], blk["ln_b"], 1e-6, b, h, w, c)
                     r += b * h * w
-                L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
-                L.gemm(hid, blk["fc2_w"], x, m, c, 4 * c, bias=blk["fc2_b"], gamma=blk["gamma"], residual=x, ldr=c,
-                       backend=backend)
+                if fused:
+                    L.mlp_fused(y, blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], blk["gamma"], x, m, c)
+                else:
+                    L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
+                    L.gemm(hid, blk["fc2_w"], x, m, c, 4 * c, bias=blk["fc2_b"], gamma=blk["gamma"], residual=x,
+                           ldr=c, backend=backend)
         c = DIMS[3]
         n_img = sum(b for b, _, _ in segs)
         pooled = _empty((n_img, c), dt, dev)

@@ -22,7 +22,7 @@ GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 EXPORTS = [
-    "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_dwconv7_ln", "gcv_ln_patchify2",
+    "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_dwconv7_ln", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
     "gcv_im2col3x3", "gcv_maxpool2", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
 ]
@@ -59,6 +59,8 @@ def load():
     lib.gcv_last_error.restype = C.c_char_p
     lib.gcv_device_supported.argtypes = [i32]
     lib.gcv_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, i64, i64, i64, C.POINTER(Epilogue), vp]
+    lib.gcv_mlp_fused_supported.argtypes = [i32, i32]
+    lib.gcv_mlp_fused.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     lib.gcv_dwconv7_ln.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
     lib.gcv_ln_patchify2.argtypes = [i32, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
     lib.gcv_stem_patchify_nchw.argtypes = [i32, vp, vp, i32, i32, i32, vp]
@@ -156,6 +158,17 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
                              _stream())
     _check(rc, f"gcv_gemm(M={M},N={N},K={K})")
     launches += 1
+
+
+def mlp_fused_supported(dtype, c):
+    return dtype in DTYPE_CODE and bool(load().gcv_mlp_fused_supported(DTYPE_CODE[dtype], c))
+
+
+def mlp_fused(y, w1, b1, w2, b2, gamma, x, M, c):
+    """x += gamma * (GELU(y @ w1^T + b1) @ w2^T + b2), in place; see gcv_mlp_fused."""
+    _run("mlp_fused", 16.0 * M * c * c, lambda: load().gcv_mlp_fused(
+        DTYPE_CODE[y.dtype], _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(x), M, c, _stream()),
+        f"M{M} C{c}")
 
 
 def dwconv7_ln(x, y, taps, bias, ln_w, ln_b, eps, B, H, W, Cc):

@@ -89,6 +89,14 @@ int gcv_device_supported(int device);      /* 1 when `device` is compute capabil
 int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
              void* D, int64_t M, int64_t N, int64_t K, const gcv_epilogue* ep, void* stream);
 
+/* Fused ConvNeXt MLP (timm ConvNeXtBlock: mlp.fc1 -> GELU -> mlp.fc2 -> * gamma -> + shortcut) for the wide-token
+ * stages: x[M,C] += gamma * (GELU(y[M,C] * W1[4C,C]^T + b1) * W2[C,4C]^T + b2), in place on x; the [M,4C] hidden
+ * activation stays in shared memory / TMEM.  bf16/fp16, C in {96,192} (gcv_mlp_fused_supported); other widths use
+ * two gcv_gemm calls. */
+int gcv_mlp_fused_supported(int dtype, int C);
+int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                  const float* gamma, void* x, int64_t M, int C, void* stream);
+
 /* -- ConvNeXt memory-bound kernels ----------------------------------------
  * gcv_dwconv7_ln: timm ConvNeXtBlock.conv_dw (7x7, pad 3, groups=C, bias) fused
  *   with ConvNeXtBlock.norm (LayerNorm over C, eps).  x,y: [B,H,W,C]; taps: [49,C].

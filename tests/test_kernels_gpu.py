@@ -102,6 +102,24 @@ def test_gemm_epilogues(dtype, backend):
     assert wide[:, :N].abs().max().item() == 0 and wide[:, 2 * N:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C", [96, 192])
+@pytest.mark.parametrize("M", [1000, 148 * 128 * 2 + 77, 128])
+def test_mlp_fused_matches_two_linear_layers(M, C, dtype):
+    """x += gamma * (GELU(y W1^T + b1) W2^T + b2): the fused kernel vs fp32 torch (hidden never leaves the SM)."""
+    L = _lib()
+    assert L.mlp_fused_supported(dtype, C) and not L.mlp_fused_supported(dtype, 384)
+    y, x = _rand(M, C, dtype=dtype, seed=1), _rand(M, C, dtype=dtype, seed=2)
+    w1 = _rand(4 * C, C, dtype=dtype, seed=3, scale=C ** -0.5)
+    w2 = _rand(C, 4 * C, dtype=dtype, seed=4, scale=(4 * C) ** -0.5)
+    b1, b2, gamma = _rand(4 * C, seed=5, scale=0.3), _rand(C, seed=6, scale=0.3), _rand(C, seed=7).abs()
+    hid = F.gelu(y.float() @ w1.float().t() + b1).to(dtype).float()       # the kernel keeps the hidden in 16-bit too
+    want = x.float() + gamma * (hid @ w2.float().t() + b2)
+    L.mlp_fused(y, w1, b1, w2, b2, gamma, x, M, C)
+    torch.cuda.synchronize()
+    _close(x, want, 2e-2 if dtype == torch.bfloat16 else 4e-3, f"mlp_fused M={M} C={C}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("cfg", [(2, 7, 7, 256, 128), (1, 14, 14, 64, 32), (2, 5, 3, 16, 3), (1, 28, 28, 32, 16)])
 def test_gemm_pixel_shuffle_is_conv_transpose(cfg, dtype):

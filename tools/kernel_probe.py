@@ -59,3 +59,12 @@ if args.which in ("fc2", "all"):
         x = torch.randn(M, C, device=dev).to(dt)
         timed(f"fc2+res M{M} N{C} K{4 * C}",
               lambda: L.gemm(a, w, x, M, C, 4 * C, bias=bias, gamma=gamma, residual=x, ldr=C), 2.0 * M * 4 * C * C / 1e3, "TF/s")
+if args.which in ("fused", "all"):
+    for (T, C) in ((3136, 96), (784, 192)):
+        M = B * T
+        y = torch.randn(M, C, device=dev).to(dt)
+        x = torch.randn(M, C, device=dev).to(dt)
+        w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).to(dt)
+        w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(dt)
+        b1, b2, g = torch.randn(4 * C, device=dev), torch.randn(C, device=dev), torch.rand(C, device=dev) * 0.1
+        timed(f"mlp_fused M{M} C{C}", lambda: L.mlp_fused(y, w1, b1, w2, b2, g, x, M, C), 16.0 * M * C * C / 1e3, "TF/s")
