@@ -2,6 +2,8 @@
 // 2x2 patchify, stem patchify, row LayerNorm, global-average-pool + LayerNorm.
 // timm==0.6.5 ConvNeXt as reached from reference model/genconvit_ed.py:68,
 // model/genconvit_vae.py:97 (arithmetic restated in oracle/backbones.py).
+#include <cuda.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -9,6 +11,24 @@
 namespace gcv {
 
 namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn dw_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
 
 // ---------------------------------------------------------------------------------
 // Depthwise 7x7 (pad 3) + bias + LayerNorm over C.
@@ -157,35 +177,73 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
 }
 
+// smem tile of one pipeline step: [group][channel box][13 pixels][CBOX channels], written by TMA
+template <int C> struct DwGeom {
+  static constexpr int CBOX = C <= 192 ? C : 192;          // TMA box dims are limited to 256 elements
+  static constexpr int NBOX = C / CBOX;
+  static_assert(C % CBOX == 0, "channel boxes");
+};
+
 template <typename T, int C>
 __global__ void __launch_bounds__(384, 1)
-dwconv7_ln_col_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ taps,
+dwconv7_ln_col_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, const float* __restrict__ taps,
                       const float* __restrict__ bias, const float* __restrict__ ln_w,
-                      const float* __restrict__ ln_b, float eps, int H, int W, int strips_w) {
-  extern __shared__ __align__(16) float dsm[];
-  float* wsm = dsm;                                       // [49][C]
-  const int n_hw = blockDim.x >> 4;                       // half-warps in the CTA
-  float* part = wsm + 49 * C;                             // [n_hw][49] per-half-warp partial statistics
-  float* tot = part + n_hw * 49;                          // [2][groups][49] mean, rstd
+                      const float* __restrict__ ln_b, float eps, int H, int W, int strips_w, int depth) {
+  using G = DwGeom<C>;
+  extern __shared__ __align__(128) uint8_t dsm_raw[];
   constexpr int half_c = C >> 1, hw_per_group = half_c >> 4;
-  const int g = threadIdx.x / half_c, c = 2 * (threadIdx.x - g * half_c);
   const int groups = blockDim.x / half_c;
+  const int n_hw = blockDim.x >> 4;                       // half-warps in the CTA
+  // layout: [barriers 128 B][taps 49*C f32][partials n_hw*49 f32][totals 2*groups*49 f32][ring depth x step_bytes]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(dsm_raw);          // [8]
+  uint64_t* empty_bar = full_bar + 8;                                  // [8]
+  float* wsm = reinterpret_cast<float*>(dsm_raw + 128);
+  float* part = wsm + 49 * C;
+  float* tot = part + n_hw * 49;
+  // every TMA box lands on a 128-byte boundary: pad the per-(group, channel box) tile
+  constexpr uint32_t tile_bytes = (13u * G::CBOX * (uint32_t)sizeof(T) + 127u) & ~127u;
+  const uint32_t step_bytes = (uint32_t)groups * G::NBOX * tile_bytes;      // smem footprint of one step
+  const uint32_t tx_bytes = (uint32_t)groups * 13 * C * (uint32_t)sizeof(T); // bytes TMA actually delivers
+  const uint32_t ring_off = (uint32_t)((128 + (49 * C + n_hw * 49 + 2 * groups * 49) * 4 + 127) & ~127);
+  const uint8_t* ring = dsm_raw + ring_off;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(dsm_raw) + ring_off;
+
+  const int g = threadIdx.x / half_c, c = 2 * (threadIdx.x - g * half_c);
   const int b = blockIdx.x / strips_w, x0 = (blockIdx.x - b * strips_w) * 7;
-  const int hw = threadIdx.x >> 4;
+  const int hw = threadIdx.x >> 4, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const bool reducer = (threadIdx.x & 15) == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < depth; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(full_bar + i)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + i)), "r"(nwarps));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // one pipeline step = the 13-pixel input row segment every row group needs next: group gg reads image row
+  // 7*gg - 3 + j at step j.  Out-of-image rows / columns are zero-filled by TMA (that IS the conv padding).
+  auto issue_step = [&](int j) {
+    const int slot = j % depth;
+    const uint32_t fb = (uint32_t)__cvta_generic_to_shared(full_bar + slot);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx_bytes) : "memory");
+    for (int gg = 0; gg < groups; ++gg)
+#pragma unroll
+      for (int cb = 0; cb < G::NBOX; ++cb) {
+        const uint32_t dst = ring_s + slot * step_bytes + (gg * G::NBOX + cb) * tile_bytes;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tm_x)), "r"(fb), "r"(cb * G::CBOX), "r"(x0 - 3),
+              "r"(7 * gg - 3 + j), "r"(b)
+            : "memory");
+      }
+  };
+  if (threadIdx.x == 0)
+    for (int j = 0; j < depth && j < 13; ++j) issue_step(j);
 
   for (int i = threadIdx.x; i < 49 * C / 4; i += blockDim.x)
     reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(taps) + i);
-
-  // 13-bit mask of the input columns x0-3 .. x0+9 that lie inside the image
-  unsigned xmask = 0;
-#pragma unroll
-  for (int ix = 0; ix < 13; ++ix) xmask |= (unsigned)(x0 + ix - 3 >= 0 && x0 + ix - 3 < W) << ix;
-
-  const int oy0 = g * 7;
-  // pointer to (row oy0-3, column x0-3, channel c); only dereferenced where the masks allow
-  const T* rowp = x + (((int64_t)b * H + (oy0 - 3)) * W + (x0 - 3)) * C + c;
-  const int64_t row_stride = (int64_t)W * C;
   const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + c));
   float2 acc[7][7];
 #pragma unroll
@@ -193,37 +251,52 @@ dwconv7_ln_col_kernel(const T* __restrict__ x, T* __restrict__ y, const float* _
 #pragma unroll
     for (int i = 0; i < 7; ++i) acc[r][i] = bv;
   const float* wbase = wsm + c;
+  // this thread's channel pair inside a step tile
+  const uint32_t my_off = (g * G::NBOX + c / G::CBOX) * tile_bytes + (c % G::CBOX) * (uint32_t)sizeof(T);
   __syncthreads();
 
 #pragma unroll
   for (int j = 0; j < 13; ++j) {
-    const int iy = oy0 - 3 + j;
-    if (iy + 1 >= 0 && iy + 1 < H && j < 12) {
-      // pull the next input row into L1 while this row's 343 FFMA2 issue (rows mostly come from L2)
-      const T* nxt = rowp + row_stride;
-#pragma unroll
-      for (int ix = 0; ix < 13; ++ix)
-        if (xmask >> ix & 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + ix * C));
+    const int slot = j % depth;
+    const uint32_t parity = (uint32_t)(j / depth) & 1u;
+    {
+      const uint32_t fb = (uint32_t)__cvta_generic_to_shared(full_bar + slot);
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(fb), "r"(parity) : "memory");
     }
-    if (iy >= 0 && iy < H) {
-      float2 v[13];
+    float2 v[13];
+    const uint8_t* src = ring + slot * step_bytes + my_off;
 #pragma unroll
-      for (int ix = 0; ix < 13; ++ix)
-        v[ix] = (xmask >> ix & 1) ? ld_pair<T>(rowp + ix * C) : make_float2(0.0f, 0.0f);
+    for (int ix = 0; ix < 13; ++ix) {
+      if constexpr (sizeof(T) == 4) v[ix] = *reinterpret_cast<const float2*>(src + ix * G::CBOX * 4);
+      else v[ix] = unpack2<T>(*reinterpret_cast<const uint32_t*>(src + ix * G::CBOX * 2));
+    }
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + slot)) : "memory");
+    if (threadIdx.x == 0 && j + depth < 13) {
+      // refill this slot with step j+depth once every warp has copied step j into registers
+      const uint32_t eb = (uint32_t)__cvta_generic_to_shared(empty_bar + slot);
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(eb), "r"(parity) : "memory");
+      issue_step(j + depth);
+    }
 #pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        const int dy = j - r;
-        if (dy >= 0 && dy < 7) {
+    for (int r = 0; r < 7; ++r) {
+      const int dy = j - r;
+      if (dy >= 0 && dy < 7) {
 #pragma unroll
-          for (int dx = 0; dx < 7; ++dx) {
-            const float2 wv = *reinterpret_cast<const float2*>(wbase + (dy * 7 + dx) * C);
+        for (int dx = 0; dx < 7; ++dx) {
+          const float2 wv = *reinterpret_cast<const float2*>(wbase + (dy * 7 + dx) * C);
 #pragma unroll
-            for (int ox = 0; ox < 7; ++ox) ffma2(acc[r][ox], v[ox + dx], wv);
-          }
+          for (int ox = 0; ox < 7; ++ox) ffma2(acc[r][ox], v[ox + dx], wv);
         }
       }
     }
-    rowp += row_stride;
   }
 
   // ---- LayerNorm statistics: mean ----
@@ -267,6 +340,8 @@ dwconv7_ln_col_kernel(const T* __restrict__ x, T* __restrict__ y, const float* _
   __syncthreads();
   const float2 gw = __ldg(reinterpret_cast<const float2*>(ln_w + c));
   const float2 gb = __ldg(reinterpret_cast<const float2*>(ln_b + c));
+  const int oy0 = g * 7;
+  const int64_t row_stride = (int64_t)W * C;
   T* yp = y + (((int64_t)b * H + oy0) * W + x0) * C + c;
 #pragma unroll
   for (int r = 0; r < 7; ++r) {
@@ -485,23 +560,63 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
                const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream) {
   GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
   const int groups = (H + 6) / 7;
-  if ((C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384) {
+  bool col_ok = (C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384;
+  if (col_ok) {
+    // the TMA-fed column kernel needs the taps plus at least two pipeline steps in shared memory
+    const size_t es0 = dtype == GCV_F32 ? 4 : 2;
+    const int cb0 = C <= 192 ? C : 192;
+    const size_t fixed0 = (128 + (size_t)(49 * C + (groups * (C / 2) / 16) * 49 + 2 * groups * 49) * 4 + 127) & ~(size_t)127;
+    const size_t step0 = (size_t)groups * (C / cb0) * ((13 * cb0 * es0 + 127) & ~(size_t)127);
+    col_ok = fixed0 + 2 * step0 <= 220 * 1024;
+  }
+  if (col_ok) {
     const int strips_w = (W + 6) / 7;
     const int64_t grid = (int64_t)B * strips_w;
     GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
+    GCV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "dwconv7_ln: x must be 16-byte aligned");
     const int threads = groups * (C / 2);
-    const size_t smem = (size_t)(49 * C + (threads / 16) * 49 + 2 * groups * 49) * sizeof(float);
+    const size_t es = dtype == GCV_F32 ? 4 : 2;
+    const size_t fixed = (128 + (size_t)(49 * C + (threads / 16) * 49 + 2 * groups * 49) * 4 + 127) & ~(size_t)127;
+    const int cbox_h = C <= 192 ? C : 192;
+    const size_t step_bytes = (size_t)groups * (C / cbox_h) * ((13 * cbox_h * es + 127) & ~(size_t)127);
+    int depth = (int)((220 * 1024 - fixed) / step_bytes);
+    if (depth > 8) depth = 8;
+    GCV_REQUIRE(depth >= 2, "dwconv7_ln: not enough shared memory for C=%d", C);
+    const size_t smem = fixed + depth * step_bytes;
+    // 4-D view [B][H][W][C] of the NHWC activation; box = (channel box, 13 pixels, 1 row, 1 image)
+    CUtensorMap tm;
+    {
+      EncodeTiledFn enc = dw_get_encode();
+      if (!enc) {
+        set_error("cuTensorMapEncodeTiled not resolvable (no CUDA driver?)");
+        return GCV_ERR_NO_DRIVER;
+      }
+      const int cbox = C <= 192 ? C : 192;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+      cuuint32_t box[4] = {(cuuint32_t)cbox, 13, 1, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUtensorMapDataType tdt = dtype == GCV_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : dtype == GCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      CUresult r = enc(&tm, tdt, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("dwconv7_ln: cuTensorMapEncodeTiled failed: CUresult %d (B=%d H=%d W=%d C=%d)", (int)r, B, H, W, C);
+        return GCV_ERR_CUDA;
+      }
+    }
     return dispatch(dtype, [&](auto tag) -> int {
       using T = decltype(tag);
       auto launch = [&](auto cc) -> int {
         constexpr int CC = decltype(cc)::value;
         static bool attr_done = false;
         if (!attr_done) {
-          cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
           attr_done = true;
         }
         dwconv7_ln_col_kernel<T, CC><<<(unsigned)grid, threads, smem, stream>>>(
-            reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w);
+            tm, reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w, depth);
         return check_launch("dwconv7_ln");
       };
       switch (C) {

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenconvit_b200.so")
+LIB_PATH = os.environ.get("GCV_LIB") or os.path.join(_HERE, "libgenconvit_b200.so")   # GCV_LIB: A/B builds in tools/
 
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY = 0, 1, 2, 3
