@@ -181,51 +181,72 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 template <int C> struct DwGeom {
   static constexpr int CBOX = C <= 192 ? C : 192;          // TMA box dims are limited to 256 elements
   static constexpr int NBOX = C / CBOX;
+  // LayerNorm statistics through a transposed smem buffer (49 floats per thread) when it fits next to the taps
+  // and the input ring; the widest stage (C = 768: 150 KB of taps) keeps the half-warp shuffle reduction
+  static constexpr bool SMEM_STATS = C <= 384;
   static_assert(C % CBOX == 0, "channel boxes");
 };
 
+__device__ __forceinline__ void dw_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+
+// Persistent: one CTA per SM walks over (image, 7-pixel column strip) work items.  The taps are fetched once per CTA
+// with a bulk async copy; the TMA input ring runs ahead across strip boundaries, so neither the ~microsecond
+// memory latency nor the per-strip prologue is exposed.
 template <typename T, int C>
 __global__ void __launch_bounds__(384, 1)
 dwconv7_ln_col_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, const float* __restrict__ taps,
                       const float* __restrict__ bias, const float* __restrict__ ln_w,
-                      const float* __restrict__ ln_b, float eps, int H, int W, int strips_w, int depth) {
+                      const float* __restrict__ ln_b, float eps, int H, int W, int strips_w, int n_strips, int depth) {
   using G = DwGeom<C>;
   extern __shared__ __align__(128) uint8_t dsm_raw[];
   constexpr int half_c = C >> 1, hw_per_group = half_c >> 4;
   const int groups = blockDim.x / half_c;
   const int n_hw = blockDim.x >> 4;                       // half-warps in the CTA
-  // layout: [barriers 128 B][taps 49*C f32][partials n_hw*49 f32][totals 2*groups*49 f32][ring depth x step_bytes]
+  // layout: [barriers 256 B][taps 49*C f32][seg partials n_hw*49 f32][totals 2*groups*49 f32]
+  //         [thread partials blockDim*49 f32 (SMEM_STATS)][ring depth x step_bytes]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(dsm_raw);          // [8]
   uint64_t* empty_bar = full_bar + 8;                                  // [8]
-  float* wsm = reinterpret_cast<float*>(dsm_raw + 128);
+  uint64_t* w_bar = full_bar + 16;
+  float* wsm = reinterpret_cast<float*>(dsm_raw + 256);
   float* part = wsm + 49 * C;
   float* tot = part + n_hw * 49;
-  // every TMA box lands on a 128-byte boundary: pad the per-(group, channel box) tile
+  float* tpart = tot + 2 * groups * 49;
   constexpr uint32_t tile_bytes = (13u * G::CBOX * (uint32_t)sizeof(T) + 127u) & ~127u;
   const uint32_t step_bytes = (uint32_t)groups * G::NBOX * tile_bytes;      // smem footprint of one step
   const uint32_t tx_bytes = (uint32_t)groups * 13 * C * (uint32_t)sizeof(T); // bytes TMA actually delivers
-  const uint32_t ring_off = (uint32_t)((128 + (49 * C + n_hw * 49 + 2 * groups * 49) * 4 + 127) & ~127);
+  const uint32_t ring_off =
+      (uint32_t)((256 + (49 * C + n_hw * 49 + 2 * groups * 49 + (G::SMEM_STATS ? (int)blockDim.x * 49 : 0)) * 4 + 127) & ~127);
   const uint8_t* ring = dsm_raw + ring_off;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(dsm_raw) + ring_off;
 
   const int g = threadIdx.x / half_c, c = 2 * (threadIdx.x - g * half_c);
-  const int b = blockIdx.x / strips_w, x0 = (blockIdx.x - b * strips_w) * 7;
   const int hw = threadIdx.x >> 4, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const bool reducer = (threadIdx.x & 15) == 0;
+  const int my_strips = (n_strips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_steps = my_strips * 13;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < depth; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(full_bar + i)), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + i)), "r"(nwarps));
     }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(w_bar)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // one pipeline step = the 13-pixel input row segment every row group needs next: group gg reads image row
-  // 7*gg - 3 + j at step j.  Out-of-image rows / columns are zero-filled by TMA (that IS the conv padding).
-  auto issue_step = [&](int j) {
-    const int slot = j % depth;
+  // one pipeline step = the 13-pixel input row segment every row group needs next: for the strip's step j, group gg
+  // reads image row 7*gg - 3 + j.  Out-of-image rows / columns are zero-filled by TMA (that IS the conv padding).
+  auto issue_step = [&](int n) {
+    const int si = n / 13, j = n - si * 13;
+    const int strip = (int)blockIdx.x + si * (int)gridDim.x;
+    const int sb = strip / strips_w, sx0 = (strip - sb * strips_w) * 7;
+    const int slot = n % depth;
     const uint32_t fb = (uint32_t)__cvta_generic_to_shared(full_bar + slot);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx_bytes) : "memory");
     for (int gg = 0; gg < groups; ++gg)
@@ -234,130 +255,146 @@ dwconv7_ln_col_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ 
         const uint32_t dst = ring_s + slot * step_bytes + (gg * G::NBOX + cb) * tile_bytes;
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tm_x)), "r"(fb), "r"(cb * G::CBOX), "r"(x0 - 3),
-              "r"(7 * gg - 3 + j), "r"(b)
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tm_x)), "r"(fb), "r"(cb * G::CBOX), "r"(sx0 - 3),
+              "r"(7 * gg - 3 + j), "r"(sb)
             : "memory");
       }
   };
-  if (threadIdx.x == 0)
-    for (int j = 0; j < depth && j < 13; ++j) issue_step(j);
+  if (threadIdx.x == 0) {
+    const uint32_t wb = (uint32_t)__cvta_generic_to_shared(w_bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wb), "r"(49 * C * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(wsm)), "l"(reinterpret_cast<uint64_t>(taps)), "r"(49 * C * 4), "r"(wb)
+                 : "memory");
+    for (int n = 0; n < depth && n < total_steps; ++n) issue_step(n);
+  }
 
-  for (int i = threadIdx.x; i < 49 * C / 4; i += blockDim.x)
-    reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(taps) + i);
   const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + c));
-  float2 acc[7][7];
-#pragma unroll
-  for (int r = 0; r < 7; ++r)
-#pragma unroll
-    for (int i = 0; i < 7; ++i) acc[r][i] = bv;
-  const float* wbase = wsm + c;
-  // this thread's channel pair inside a step tile
-  const uint32_t my_off = (g * G::NBOX + c / G::CBOX) * tile_bytes + (c % G::CBOX) * (uint32_t)sizeof(T);
-  __syncthreads();
-
-#pragma unroll
-  for (int j = 0; j < 13; ++j) {
-    const int slot = j % depth;
-    const uint32_t parity = (uint32_t)(j / depth) & 1u;
-    {
-      const uint32_t fb = (uint32_t)__cvta_generic_to_shared(full_bar + slot);
-      uint32_t ok = 0;
-      while (!ok)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(fb), "r"(parity) : "memory");
-    }
-    float2 v[13];
-    const uint8_t* src = ring + slot * step_bytes + my_off;
-#pragma unroll
-    for (int ix = 0; ix < 13; ++ix) {
-      if constexpr (sizeof(T) == 4) v[ix] = *reinterpret_cast<const float2*>(src + ix * G::CBOX * 4);
-      else v[ix] = unpack2<T>(*reinterpret_cast<const uint32_t*>(src + ix * G::CBOX * 2));
-    }
-    __syncwarp();
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + slot)) : "memory");
-    if (threadIdx.x == 0 && j + depth < 13) {
-      // refill this slot with step j+depth once every warp has copied step j into registers
-      const uint32_t eb = (uint32_t)__cvta_generic_to_shared(empty_bar + slot);
-      uint32_t ok = 0;
-      while (!ok)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(eb), "r"(parity) : "memory");
-      issue_step(j + depth);
-    }
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int dy = j - r;
-      if (dy >= 0 && dy < 7) {
-#pragma unroll
-        for (int dx = 0; dx < 7; ++dx) {
-          const float2 wv = *reinterpret_cast<const float2*>(wbase + (dy * 7 + dx) * C);
-#pragma unroll
-          for (int ox = 0; ox < 7; ++ox) ffma2(acc[r][ox], v[ox + dx], wv);
-        }
-      }
-    }
-  }
-
-  // ---- LayerNorm statistics: mean ----
-#pragma unroll
-  for (int r = 0; r < 7; ++r)
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      float t = acc[r][i].x + acc[r][i].y;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (reducer) part[hw * 49 + r * 7 + i] = t;
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < groups * 49; i += blockDim.x) {
-    const int gg = i / 49, px = i - gg * 49;
-    float t = 0.0f;
-#pragma unroll
-    for (int k = 0; k < hw_per_group; ++k) t += part[(gg * hw_per_group + k) * 49 + px];
-    tot[i] = t * (1.0f / (float)C);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 7; ++r)
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const float mean = tot[g * 49 + r * 7 + i];
-      acc[r][i].x -= mean; acc[r][i].y -= mean;
-      float t = acc[r][i].x * acc[r][i].x + acc[r][i].y * acc[r][i].y;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (reducer) part[hw * 49 + r * 7 + i] = t;       // safe: every read of the mean partials is behind a barrier
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < groups * 49; i += blockDim.x) {
-    const int gg = i / 49, px = i - gg * 49;
-    float t = 0.0f;
-#pragma unroll
-    for (int k = 0; k < hw_per_group; ++k) t += part[(gg * hw_per_group + k) * 49 + px];
-    tot[groups * 49 + i] = rsqrtf(t * (1.0f / (float)C) + eps);
-  }
-  __syncthreads();
   const float2 gw = __ldg(reinterpret_cast<const float2*>(ln_w + c));
   const float2 gb = __ldg(reinterpret_cast<const float2*>(ln_b + c));
-  const int oy0 = g * 7;
+  const float* wbase = wsm + c;
+  const uint32_t my_off = (g * G::NBOX + c / G::CBOX) * tile_bytes + (c % G::CBOX) * (uint32_t)sizeof(T);
   const int64_t row_stride = (int64_t)W * C;
-  T* yp = y + (((int64_t)b * H + oy0) * W + x0) * C + c;
+  const int oy0 = g * 7;
+  dw_mbar_wait((uint32_t)__cvta_generic_to_shared(w_bar), 0);          // taps have landed
+
+  int slot = 0;
+  uint32_t parity = 0;
+  int n = 0;
+  for (int si = 0; si < my_strips; ++si) {
+    const int strip = (int)blockIdx.x + si * (int)gridDim.x;
+    const int b = strip / strips_w, x0 = (strip - b * strips_w) * 7;
+    float2 acc[7][7];
 #pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    if (oy0 + r < H) {
+    for (int r = 0; r < 7; ++r)
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        if (x0 + i < W) {
-          const float rstd = tot[groups * 49 + g * 49 + r * 7 + i];
-          const float o0 = acc[r][i].x * rstd * gw.x + gb.x, o1 = acc[r][i].y * rstd * gw.y + gb.y;
-          T* dst = yp + i * C;
-          if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-          else *reinterpret_cast<uint32_t*>(dst) = pack2<T>(o0, o1);
+      for (int i = 0; i < 7; ++i) acc[r][i] = bv;
+
+#pragma unroll
+    for (int j = 0; j < 13; ++j, ++n) {
+      dw_mbar_wait((uint32_t)__cvta_generic_to_shared(full_bar + slot), parity);
+      float2 v[13];
+      const uint8_t* src = ring + slot * step_bytes + my_off;
+#pragma unroll
+      for (int ix = 0; ix < 13; ++ix) {
+        if constexpr (sizeof(T) == 4) v[ix] = *reinterpret_cast<const float2*>(src + ix * G::CBOX * 4);
+        else v[ix] = unpack2<T>(*reinterpret_cast<const uint32_t*>(src + ix * G::CBOX * 2));
+      }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + slot)) : "memory");
+      if (threadIdx.x == 0 && n + depth < total_steps) {
+        // refill this slot with step n+depth once every warp has copied step n into registers
+        dw_mbar_wait((uint32_t)__cvta_generic_to_shared(empty_bar + slot), parity);
+        issue_step(n + depth);
+      }
+      if (++slot == depth) { slot = 0; parity ^= 1; }
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const int dy = j - r;
+        if (dy >= 0 && dy < 7) {
+#pragma unroll
+          for (int dx = 0; dx < 7; ++dx) {
+            const float2 wv = *reinterpret_cast<const float2*>(wbase + (dy * 7 + dx) * C);
+#pragma unroll
+            for (int ox = 0; ox < 7; ++ox) ffma2(acc[r][ox], v[ox + dx], wv);
+          }
         }
       }
     }
-    yp += row_stride;
+
+    // ---- LayerNorm statistics, exact two-pass, deterministic ----
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if constexpr (G::SMEM_STATS) {
+        // every thread parks its 49 per-pixel partials (row of 49 floats: odd stride, conflict-free both ways);
+        // 16-thread segment sums and group totals are then plain strided smem reads instead of 392 shuffles
+        float* mine = tpart + threadIdx.x * 49;
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+          for (int i = 0; i < 7; ++i)
+            mine[r * 7 + i] = pass == 0 ? acc[r][i].x + acc[r][i].y
+                                        : acc[r][i].x * acc[r][i].x + acc[r][i].y * acc[r][i].y;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_hw * 49; i += blockDim.x) {
+          const int seg = i / 49, px = i - seg * 49;
+          const float* col = tpart + seg * 16 * 49 + px;
+          float t = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) t += col[k * 49];
+          part[i] = t;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            float t = pass == 0 ? acc[r][i].x + acc[r][i].y
+                                : acc[r][i].x * acc[r][i].x + acc[r][i].y * acc[r][i].y;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (reducer) part[hw * 49 + r * 7 + i] = t;
+          }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < groups * 49; i += blockDim.x) {
+        const int gg = i / 49, px = i - gg * 49;
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < hw_per_group; ++k) t += part[(gg * hw_per_group + k) * 49 + px];
+        tot[pass * groups * 49 + i] = pass == 0 ? t * (1.0f / (float)C) : rsqrtf(t * (1.0f / (float)C) + eps);
+      }
+      __syncthreads();
+      if (pass == 0) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const float mean = tot[g * 49 + r * 7 + i];
+            acc[r][i].x -= mean; acc[r][i].y -= mean;
+          }
+      }
+    }
+    T* yp = y + (((int64_t)b * H + oy0) * W + x0) * C + c;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      if (oy0 + r < H) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          if (x0 + i < W) {
+            const float rstd = tot[groups * 49 + g * 49 + r * 7 + i];
+            const float o0 = acc[r][i].x * rstd * gw.x + gb.x, o1 = acc[r][i].y * rstd * gw.y + gb.y;
+            T* dst = yp + i * C;
+            if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+            else *reinterpret_cast<uint32_t*>(dst) = pack2<T>(o0, o1);
+          }
+        }
+      }
+      yp += row_stride;
+    }
+    // the next strip's first statistics write to tpart / part / tot happens after its 13 barrier-free steps and is
+    // ordered behind this strip's last reads by the barriers above plus the barrier that follows that write
   }
 }
 
@@ -560,29 +597,29 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
                const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream) {
   GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
   const int groups = (H + 6) / 7;
-  bool col_ok = (C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384;
-  if (col_ok) {
-    // the TMA-fed column kernel needs the taps plus at least two pipeline steps in shared memory
-    const size_t es0 = dtype == GCV_F32 ? 4 : 2;
-    const int cb0 = C <= 192 ? C : 192;
-    const size_t fixed0 = (128 + (size_t)(49 * C + (groups * (C / 2) / 16) * 49 + 2 * groups * 49) * 4 + 127) & ~(size_t)127;
-    const size_t step0 = (size_t)groups * (C / cb0) * ((13 * cb0 * es0 + 127) & ~(size_t)127);
-    col_ok = fixed0 + 2 * step0 <= 220 * 1024;
-  }
-  if (col_ok) {
+  const bool col_shape = (C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384;
+  const size_t es = dtype == GCV_F32 ? 4 : 2;
+  const int threads = groups * (C / 2);
+  const int cbox = C <= 192 ? C : 192;
+  const size_t fixed = col_shape ? ((256 + (size_t)(49 * C + (threads / 16) * 49 + 2 * groups * 49 +
+                                                     (C <= 384 ? threads * 49 : 0)) * 4 + 127) & ~(size_t)127) : 0;
+  const size_t step_bytes = col_shape ? (size_t)groups * (C / cbox) * ((13 * cbox * es + 127) & ~(size_t)127) : 1;
+  // the TMA-fed column kernel needs the taps (+ statistics buffer) plus at least two pipeline steps in shared memory
+  if (col_shape && fixed + 2 * step_bytes <= 224 * 1024) {
     const int strips_w = (W + 6) / 7;
-    const int64_t grid = (int64_t)B * strips_w;
-    GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
+    const int64_t n_strips = (int64_t)B * strips_w;
+    GCV_REQUIRE(n_strips < 2147483647LL / 13, "dwconv7_ln: too many strips");
     GCV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "dwconv7_ln: x must be 16-byte aligned");
-    const int threads = groups * (C / 2);
-    const size_t es = dtype == GCV_F32 ? 4 : 2;
-    const size_t fixed = (128 + (size_t)(49 * C + (threads / 16) * 49 + 2 * groups * 49) * 4 + 127) & ~(size_t)127;
-    const int cbox_h = C <= 192 ? C : 192;
-    const size_t step_bytes = (size_t)groups * (C / cbox_h) * ((13 * cbox_h * es + 127) & ~(size_t)127);
-    int depth = (int)((220 * 1024 - fixed) / step_bytes);
+    int depth = (int)((224 * 1024 - fixed) / step_bytes);
     if (depth > 8) depth = 8;
-    GCV_REQUIRE(depth >= 2, "dwconv7_ln: not enough shared memory for C=%d", C);
     const size_t smem = fixed + depth * step_bytes;
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = (int)(n_strips < sms ? n_strips : sms);
     // 4-D view [B][H][W][C] of the NHWC activation; box = (channel box, 13 pixels, 1 row, 1 image)
     CUtensorMap tm;
     {
@@ -591,7 +628,6 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
         set_error("cuTensorMapEncodeTiled not resolvable (no CUDA driver?)");
         return GCV_ERR_NO_DRIVER;
       }
-      const int cbox = C <= 192 ? C : 192;
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
       cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
       cuuint32_t box[4] = {(cuuint32_t)cbox, 13, 1, 1};
@@ -612,11 +648,11 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
         constexpr int CC = decltype(cc)::value;
         static bool attr_done = false;
         if (!attr_done) {
-          cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+          cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
           attr_done = true;
         }
-        dwconv7_ln_col_kernel<T, CC><<<(unsigned)grid, threads, smem, stream>>>(
-            tm, reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w, depth);
+        dwconv7_ln_col_kernel<T, CC><<<grid, threads, smem, stream>>>(
+            tm, reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w, (int)n_strips, depth);
         return check_launch("dwconv7_ln");
       };
       switch (C) {
