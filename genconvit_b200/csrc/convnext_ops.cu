@@ -303,10 +303,13 @@ dwconv7_ln_col_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ 
       __syncwarp();
       if (lane == 0)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(empty_bar + slot)) : "memory");
-      if (threadIdx.x == 0 && n + depth < total_steps) {
-        // refill this slot with step n+depth once every warp has copied step n into registers
-        dw_mbar_wait((uint32_t)__cvta_generic_to_shared(empty_bar + slot), parity);
-        issue_step(n + depth);
+      if (threadIdx.x == 0 && n >= 1 && n - 1 + depth < total_steps) {
+        // refill the slot of the PREVIOUS step (every warp has long copied it into registers by now, so this
+        // wait almost never blocks warp 0) with step n-1+depth
+        const int pslot = slot == 0 ? depth - 1 : slot - 1;
+        const uint32_t pparity = slot == 0 ? parity ^ 1 : parity;
+        dw_mbar_wait((uint32_t)__cvta_generic_to_shared(empty_bar + pslot), pparity);
+        issue_step(n - 1 + depth);
       }
       if (++slot == depth) { slot = 0; parity ^= 1; }
 #pragma unroll
