@@ -49,6 +49,7 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
 bool mlp_fused_supported(int dtype, int C);
+int mlp_fused_trace(long long* out64);
 int mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
               const float* gamma, void* x, int64_t M, int C, cudaStream_t stream);
 
@@ -95,6 +96,8 @@ int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, 
   return GCV_ERR_BAD_ARG;
 }
 
+// debug builds only (-DGCV_FUSED_TRACE): copies 64 cycle counters of the last fused-MLP launch; returns 0 otherwise
+int gcv_debug_fused_trace(long long* out64) { return mlp_fused_trace(out64); }
 int gcv_mlp_fused_supported(int dtype, int C) { return mlp_fused_supported(dtype, C) ? 1 : 0; }
 int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, void* x, int64_t M, int C, void* stream) {

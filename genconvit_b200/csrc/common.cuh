@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/genconvit_b200.h"
 
 namespace gcv {
@@ -95,6 +97,36 @@ __device__ __forceinline__ float gelu_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float h = 0.5f * x;
   return fmaf(h, t, h);
+}
+
+// The same GELU on a pair of values in packed fp16 arithmetic (HMUL2/HFMA2 + one tanh.approx.f16x2 for both):
+// 6 instructions per PAIR.  fp16 carries 11 significant bits, comfortably below the 16-bit output rounding;
+// |x| > 255 overflows x*x to +inf, which still yields the correct limits (x or 0) through tanh(+-inf) = +-1.
+__device__ __forceinline__ __half2 gelu_fast_h2(__half2 x) {
+  const __half2 c1 = __float2half2_rn(8.0015698e-1f), c3 = __float2half2_rn(3.470094e-2f), hf = __float2half2_rn(0.5f);
+  const __half2 u = __hmul2(x, __hfma2(__hmul2(x, x), c3, c1));
+  __half2 t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(*reinterpret_cast<uint32_t*>(&t)) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 h = __hmul2(x, hf);
+  return __hfma2(h, t, h);
+}
+
+// bias + GELU on 8 fp32 accumulators -> 8 packed 16-bit outputs (T = __half or __nv_bfloat16)
+template <typename T>
+__device__ __forceinline__ uint4 bias_gelu_pack8(const float* w, const float4 b0, const float4 b1) {
+  const __half2 g0 = gelu_fast_h2(__floats2half2_rn(w[0] + b0.x, w[1] + b0.y));
+  const __half2 g1 = gelu_fast_h2(__floats2half2_rn(w[2] + b0.z, w[3] + b0.w));
+  const __half2 g2 = gelu_fast_h2(__floats2half2_rn(w[4] + b1.x, w[5] + b1.y));
+  const __half2 g3 = gelu_fast_h2(__floats2half2_rn(w[6] + b1.z, w[7] + b1.w));
+  uint4 q;
+  if constexpr (sizeof(T) == 2 && !std::is_same<T, __half>::value) {
+    const float2 f0 = __half22float2(g0), f1 = __half22float2(g1), f2 = __half22float2(g2), f3 = __half22float2(g3);
+    q.x = pack2<T>(f0.x, f0.y); q.y = pack2<T>(f1.x, f1.y); q.z = pack2<T>(f2.x, f2.y); q.w = pack2<T>(f3.x, f3.y);
+  } else {
+    q.x = *reinterpret_cast<const uint32_t*>(&g0); q.y = *reinterpret_cast<const uint32_t*>(&g1);
+    q.z = *reinterpret_cast<const uint32_t*>(&g2); q.w = *reinterpret_cast<const uint32_t*>(&g3);
+  }
+  return q;
 }
 
 __device__ __forceinline__ float apply_act_fast(float v, int act) {

@@ -184,6 +184,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int sub = ew >> 2;                             // the 4 warps of a quarter take chunks sub, sub+4, ...
     const int chunks = p.block_n / 32;
     const bool vec_ok = p.vec_ok != 0;
+    // bias + GELU and nothing else (the ConvNeXt fc1 shape): packed-half epilogue
+    const bool gelu_only = vec_ok && p.vec_smem && p.ep.act == GCV_ACT_GELU && p.ep.bias && !p.ep.gamma && !p.ep.residual;
     uint8_t* my_stage = stage_base + ew * kStageWarp;
     const gcv_epilogue& ep = p.ep;
     int as = -1;
@@ -237,7 +239,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int j = 0; j < 4; ++j) {
           const int n = n0 + j * 8;
           float* w = v + j * 8;
-          if (n + 8 <= p.N) {
+          if (gelu_only && n + 8 <= p.N) {
+            // fc1 fast path: bias + GELU in packed fp16 arithmetic, done at pack time below
+          } else if (n + 8 <= p.N) {
             if (p.vec_smem) {
               if (ep.bias) {
                 const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n);
@@ -275,8 +279,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               epilogue_slow8<T>(ep, m, n, p.N, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], D);
           }
           uint4 q;
-          q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
-          q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
+          if (gelu_only && n + 8 <= p.N) {
+            q = bias_gelu_pack8<T>(v + j * 8, *reinterpret_cast<const float4*>(vec_bias + n),
+                                   *reinterpret_cast<const float4*>(vec_bias + n + 4));
+          } else {
+            q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
+            q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
+          }
           *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
         }
         __syncwarp();

@@ -47,11 +47,16 @@ struct Cfg {
   static constexpr int SLOT = 3 * FBLK;
   static constexpr int KB1 = 3, P1 = XKB / KB1;              // W1 chunk = P1 slots
   static constexpr int KB2 = SLOT / (C * 64), P2 = HKB / KB2; // W2 chunk = P2 slots
-  static constexpr int RING = C <= 96 ? 5 : 4;
-  static_assert(XKB % KB1 == 0 && KB2 * C * 64 == SLOT && HKB % KB2 == 0, "slot geometry");
+  // the chunk pipeline runs across tile boundaries: that needs the next tile's y block and (TMEM permitting) a
+  // second output accumulator
+  static constexpr int XBUF = 1;   // fc1 runs two chunks ahead, which hides the reload of the single y buffer
+  static constexpr int OBUF = (2 * FCH + 2 * C <= 512) ? 2 : 1;
+  static constexpr int RING = C <= 96 ? 4 : 3;
+  static constexpr int STAGE_BYTES = kFEpiWarps * 32 * 64;   // per-warp 32 x 64 B output staging tiles
   static constexpr int VEC_BYTES = ((HC + 2 * C) * 4 + 1023) / 1024 * 1024;
-  static constexpr int SMEM = kFCtrl + VEC_BYTES + X_BYTES + 2 * H_BYTES + RING * SLOT + 1024;
-  static_assert(C % 32 == 0 && C <= 192 && HC % FCH == 0, "unsupported width");
+  static constexpr int SMEM = kFCtrl + VEC_BYTES + XBUF * X_BYTES + 2 * H_BYTES + RING * SLOT + STAGE_BYTES + 1024;
+  static_assert(C % 32 == 0 && C <= 192 && HC % FCH == 0 && NCH >= 2, "unsupported width");
+  static_assert(XKB % KB1 == 0 && KB2 * C * 64 == SLOT && HKB % KB2 == 0, "slot geometry");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -65,6 +70,20 @@ struct FParams {
   void* x;                 // [M, C] residual in / result out (in place)
 };
 
+#ifdef GCV_FUSED_TRACE
+// debug build: per-role cycle counters of CTA 0 (wait sites + total), dumped to gcv_fused_trace[]
+__device__ long long gcv_fused_trace[64];
+#define TR_DECL long long tr_t0 = 0; long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tr_start = clock64();
+#define TR_BEGIN tr_t0 = clock64();
+#define TR_END(i) tr_acc[i] += clock64() - tr_t0;
+#define TR_DUMP(base) if (blockIdx.x == 0) { for (int i_ = 0; i_ < 7; ++i_) gcv_fused_trace[(base) + i_] = tr_acc[i_]; gcv_fused_trace[(base) + 7] = clock64() - tr_start; }
+#else
+#define TR_DECL
+#define TR_BEGIN
+#define TR_END(i)
+#define TR_DUMP(base)
+#endif
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T, int C>
@@ -77,36 +96,39 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   // control block
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbase);
-  uint64_t* x_full = bars + 0;
-  uint64_t* x_empty = bars + 1;
-  uint64_t* o_full = bars + 2;
-  uint64_t* o_empty = bars + 3;
-  uint64_t* s_full = bars + 4;        // [2]
-  uint64_t* s_empty = bars + 6;       // [2]
-  uint64_t* h_full = bars + 8;        // [2]
-  uint64_t* h_empty = bars + 10;      // [2]
-  uint64_t* ring_full = bars + 12;    // [RING]
-  uint64_t* ring_empty = bars + 12 + K::RING;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * K::RING);
+  uint64_t* x_full = bars + 0;        // [2]
+  uint64_t* x_empty = bars + 2;       // [2]
+  uint64_t* o_full = bars + 4;        // [2]
+  uint64_t* o_empty = bars + 6;       // [2]
+  uint64_t* s_full = bars + 8;        // [2]
+  uint64_t* s_empty = bars + 10;      // [2]
+  uint64_t* h_full = bars + 12;       // [2]
+  uint64_t* h_empty = bars + 14;      // [2]
+  uint64_t* ring_full = bars + 16;    // [RING]
+  uint64_t* ring_empty = bars + 16 + K::RING;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * K::RING);
   float* vec_b1 = reinterpret_cast<float*>(gbase + kFCtrl);           // [HC]
   float* vec_b2 = vec_b1 + K::HC;                                      // [C]
   float* vec_g = vec_b2 + C;                                           // [C]
-  const uint32_t x_smem = base + kFCtrl + K::VEC_BYTES;
-  const uint32_t h_smem = x_smem + K::X_BYTES;                         // H0, H1
+  const uint32_t x_smem = base + kFCtrl + K::VEC_BYTES;               // X0 (, X1)
+  const uint32_t h_smem = x_smem + K::XBUF * K::X_BYTES;              // H0, H1
   const uint32_t ring_smem = h_smem + 2 * K::H_BYTES;
-  uint8_t* h_gen = gbase + kFCtrl + K::VEC_BYTES + K::X_BYTES;        // generic pointer to H0
+  uint8_t* h_gen = gbase + kFCtrl + K::VEC_BYTES + K::XBUF * K::X_BYTES;   // generic pointer to H0
+  uint8_t* stage_gen = h_gen + 2 * K::H_BYTES + K::RING * K::SLOT;          // output staging, one 2 KB tile per warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * K::NCH;            // hidden chunks this CTA processes, numbered g = 0 .. total-1
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(x_full), 1);
-    mbar_init(smem_u32(x_empty), 1);
-    mbar_init(smem_u32(o_full), 1);
-    mbar_init(smem_u32(o_empty), kFEpiWarps);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(x_full + i), 1);
+      mbar_init(smem_u32(x_empty + i), 1);
+      mbar_init(smem_u32(o_full + i), 1);
+      mbar_init(smem_u32(o_empty + i), kFEpiWarps);
       mbar_init(smem_u32(s_full + i), 1);
-      mbar_init(smem_u32(s_empty + i), kFEpiWarps);
-      mbar_init(smem_u32(h_full + i), kFEpiWarps);
+      mbar_init(smem_u32(s_empty + i), kFEpiWarps / 2);     // chunk buffer i belongs to epilogue group i (8 warps)
+      mbar_init(smem_u32(h_full + i), kFEpiWarps / 2);
       mbar_init(smem_u32(h_empty + i), 1);
     }
     for (int i = 0; i < K::RING; ++i) {
@@ -130,187 +152,189 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 2 * FCH;
+  const uint32_t tmem_o = tmem_base + 2 * FCH;      // O0 (, O1 = O0 + C)
 
+  // Buffer bookkeeping shared by all roles.  Tile i of this CTA uses y buffer i % XBUF for the (i / XBUF)-th time and
+  // output accumulator i % OBUF for the (i / OBUF)-th time; chunk g uses S / H buffer g & 1 for the (g >> 1)-th time.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int slot = 0;
-      uint32_t rphase = 0, x_use = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++x_use) {
-        mbar_wait(smem_u32(x_empty), (x_use & 1) ^ 1);
-        mbar_expect_tx(smem_u32(x_full), K::X_BYTES);
+      uint32_t rphase = 0;
+      TR_DECL
+      auto issue_x = [&](int ti) {
+        const int xb = ti % K::XBUF;
+        const uint32_t use = (uint32_t)(ti / K::XBUF);
+        TR_BEGIN
+        mbar_wait(smem_u32(x_empty + xb), (use & 1) ^ 1);
+        TR_END(0)
+        mbar_expect_tx(smem_u32(x_full + xb), K::X_BYTES);
+        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
 #pragma unroll 1
         for (int kb = 0; kb < K::XKB; ++kb)
-          tma_load_2d(x_smem + kb * FBLK, &tm_y, smem_u32(x_full), kb * FKB, tile * FM);
+          tma_load_2d(x_smem + xb * K::X_BYTES + kb * FBLK, &tm_y, smem_u32(x_full + xb), kb * FKB, tile * FM);
+      };
+      if (my_tiles > 0) issue_x(0);
 #pragma unroll 1
-        for (int j = 0; j <= K::NCH; ++j) {
-          if (j < K::NCH) {
+      for (int g = 0; g < total + 2; ++g) {          // same order as the MMA warp: W1 of chunk g, then W2 of chunk g-2
+        if (g < total) {
+          const int ti = g / K::NCH, j = g - ti * K::NCH;
 #pragma unroll 1
-            for (int part = 0; part < K::P1; ++part) {
-              mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
-              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+          for (int part = 0; part < K::P1; ++part) {
+            TR_BEGIN
+            mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
+            TR_END(1)
+            mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
 #pragma unroll
-              for (int kb = 0; kb < K::KB1; ++kb)
-                tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
-                            (part * K::KB1 + kb) * FKB, j * FCH);
-              if (++slot == K::RING) { slot = 0; rphase ^= 1; }
-            }
+            for (int kb = 0; kb < K::KB1; ++kb)
+              tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
+                          (part * K::KB1 + kb) * FKB, j * FCH);
+            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
-          if (j >= 1) {
+          // next tile's y block: a whole tile ahead with two buffers, else as soon as this tile's fc1s can retire
+          if (ti + 1 < my_tiles && j == (K::XBUF == 2 ? 0 : K::NCH - 1)) issue_x(ti + 1);
+        }
+        if (g >= 2) {
+          const int gj = g - 2, jj = gj % K::NCH;
 #pragma unroll 1
-            for (int part = 0; part < K::P2; ++part) {
-              mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
-              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+          for (int part = 0; part < K::P2; ++part) {
+            TR_BEGIN
+            mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
+            TR_END(1)
+            mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
 #pragma unroll
-              for (int kb = 0; kb < K::KB2; ++kb)
-                tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
-                            (j - 1) * FCH + (part * K::KB2 + kb) * FKB, 0);
-              if (++slot == K::RING) { slot = 0; rphase ^= 1; }
-            }
+            for (int kb = 0; kb < K::KB2; ++kb)
+              tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
+                          jj * FCH + (part * K::KB2 + kb) * FKB, 0);
+            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
         }
       }
+      TR_DUMP(0)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int slot = 0;
-      // x_use = tiles done by this CTA; buffer b of S / H is used (NCH + 1 - b) / 2 times per tile, so its
-      // n-th use (n = x_use * uses_per_tile + j / 2) has mbarrier parity n & 1
-      uint32_t rphase = 0, x_use = 0, o_use = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++x_use) {
-        mbar_wait(smem_u32(x_full), x_use & 1);
-        tc_fence_after();
+      uint32_t rphase = 0;
+      TR_DECL
+      // descriptor bases: only the 14-bit start-address field changes between operands
+      const uint64_t dx0 = umma_desc_kmajor<64>(x_smem), dh0 = umma_desc_kmajor<64>(h_smem), dr0 = umma_desc_kmajor<64>(ring_smem);
+      // fc1 runs two chunks ahead of fc2: S[g & 1] is free as soon as the epilogue has pulled chunk g-2 out of TMEM,
+      // long before that chunk's GELU output is back in H -- so the next chunk's accumulator is always waiting for
+      // the epilogue group instead of the other way round
 #pragma unroll 1
-        for (int j = 0; j <= K::NCH; ++j) {
-          if (j < K::NCH) {
-            const int b = j & 1;
-            const uint32_t n_use = x_use * ((K::NCH + 1 - b) >> 1) + (j >> 1);
-            mbar_wait(smem_u32(s_empty + b), (n_use & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d = tmem_base + b * FCH;
-#pragma unroll 1
-            for (int part = 0; part < K::P1; ++part) {
-              mbar_wait(smem_u32(ring_full + slot), rphase);
-              tc_fence_after();
-#pragma unroll
-              for (int kb = 0; kb < K::KB1; ++kb) {
-                const uint32_t a = x_smem + (part * K::KB1 + kb) * FBLK, w = ring_smem + slot * K::SLOT + kb * FBLK;
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  tc_mma(d, umma_desc_kmajor<64>(a + k * 32), umma_desc_kmajor<64>(w + k * 32), p.idesc1,
-                         (part | kb | k) ? 1u : 0u);
-              }
-              tc_commit(smem_u32(ring_empty + slot));
-              if (++slot == K::RING) { slot = 0; rphase ^= 1; }
-            }
-            tc_commit(smem_u32(s_full + b));
-            if (j == K::NCH - 1) tc_commit(smem_u32(x_empty));      // y block may be overwritten by the next tile
+      for (int g = 0; g < total + 2; ++g) {
+        if (g < total) {
+          const int ti = g / K::NCH, j = g - ti * K::NCH;
+          const int xb = ti % K::XBUF;
+          if (j == 0) {
+            TR_BEGIN
+            mbar_wait(smem_u32(x_full + xb), (uint32_t)(ti / K::XBUF) & 1);
+            TR_END(0)
           }
-          if (j >= 1) {
-            const int jj = j - 1, hb = jj & 1;
-            const uint32_t n_use = x_use * ((K::NCH + 1 - hb) >> 1) + (jj >> 1);
-            mbar_wait(smem_u32(h_full + hb), n_use & 1);
-            tc_fence_after();
-            if (jj == 0) {
-              mbar_wait(smem_u32(o_empty), (o_use & 1) ^ 1);
-              tc_fence_after();
-            }
+          const int b = g & 1;
+          TR_BEGIN
+          mbar_wait(smem_u32(s_empty + b), ((uint32_t)(g >> 1) & 1) ^ 1);
+          TR_END(1)
+          tc_fence_after();
+          const uint32_t d = tmem_base + b * FCH;
 #pragma unroll 1
-            for (int part = 0; part < K::P2; ++part) {
-              mbar_wait(smem_u32(ring_full + slot), rphase);
-              tc_fence_after();
+          for (int part = 0; part < K::P1; ++part) {
+            TR_BEGIN
+            mbar_wait(smem_u32(ring_full + slot), rphase);
+            TR_END(2)
+            tc_fence_after();
+            const uint64_t da = dx0 + (uint64_t)((xb * K::X_BYTES + part * K::KB1 * FBLK) >> 4);
+            const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
 #pragma unroll
-              for (int kb = 0; kb < K::KB2; ++kb) {
-                const uint32_t a = h_smem + hb * K::H_BYTES + (part * K::KB2 + kb) * FBLK;
-                const uint32_t w = ring_smem + slot * K::SLOT + kb * (C * 64);
+            for (int kb = 0; kb < K::KB1; ++kb)
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  tc_mma(tmem_o, umma_desc_kmajor<64>(a + k * 32), umma_desc_kmajor<64>(w + k * 32), p.idesc2,
-                         (jj | part | kb | k) ? 1u : 0u);
-              }
-              tc_commit(smem_u32(ring_empty + slot));
-              if (++slot == K::RING) { slot = 0; rphase ^= 1; }
-            }
-            tc_commit(smem_u32(h_empty + hb));
-            if (jj == K::NCH - 1) {
-              tc_commit(smem_u32(o_full));
-              ++o_use;
-            }
+              for (int k = 0; k < 2; ++k)
+                tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1,
+                       (part | kb | k) ? 1u : 0u);
+            tc_commit(smem_u32(ring_empty + slot));
+            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
+          tc_commit(smem_u32(s_full + b));
+          if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));      // y buffer may be refilled
+        }
+        if (g >= 2) {
+          const int gj = g - 2, ti = gj / K::NCH, jj = gj - ti * K::NCH;
+          const int hb = gj & 1, ob = ti % K::OBUF;
+          TR_BEGIN
+          mbar_wait(smem_u32(h_full + hb), (uint32_t)(gj >> 1) & 1);
+          TR_END(3)
+          tc_fence_after();
+          if (jj == 0) {
+            TR_BEGIN
+            mbar_wait(smem_u32(o_empty + ob), ((uint32_t)(ti / K::OBUF) & 1) ^ 1);
+            TR_END(4)
+            tc_fence_after();
+          }
+          const uint32_t dout = tmem_o + ob * C;
+#pragma unroll 1
+          for (int part = 0; part < K::P2; ++part) {
+            TR_BEGIN
+            mbar_wait(smem_u32(ring_full + slot), rphase);
+            TR_END(5)
+            tc_fence_after();
+            const uint64_t da = dh0 + (uint64_t)((hb * K::H_BYTES + part * K::KB2 * FBLK) >> 4);
+            const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+#pragma unroll
+            for (int kb = 0; kb < K::KB2; ++kb)
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                tc_mma(dout, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * C * 64 + k * 32) >> 4), p.idesc2,
+                       (jj | part | kb | k) ? 1u : 0u);
+            tc_commit(smem_u32(ring_empty + slot));
+            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
+          }
+          tc_commit(smem_u32(h_empty + hb));
+          if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
         }
       }
+      TR_DUMP(8)
     }
   } else {
     // ===================== epilogue =====================
+    // The 16 warps form two groups of 8; group g owns the chunks with (chunk index & 1) == g, i.e. TMEM buffer S[g] and
+    // smem buffer H[g].  While one group sits in a TMEM-load / barrier / smem-fence latency the other one issues math.
     const int q = warp & 3;                  // TMEM lane quarter = rows 32q .. 32q+31 of the tile
-    const int s = (warp - 2) >> 2;           // K-block of the hidden chunk / column-chunk phase of O
+    const int grp = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;  // which 64 hidden columns (2 K-blocks) of the group's chunk
+    const int s = (warp - 2) >> 2;           // column-chunk phase of the O epilogue
     const int row = q * 32 + lane;
     const int sw = (row >> 1) & 3;           // 64B-swizzle XOR for this row
-    uint32_t o_use = 0, t_use = 0;          // t_use = tiles done by this CTA (same use-count arithmetic as the MMA warp)
-    uint8_t* my_stage = h_gen + s * FBLK + (q * 32) * 64;    // this warp's 32 x 64 B slice of H0 doubles as O staging
+    // output staging tile of this warp (dedicated: the drain of tile t overlaps H traffic of tile t+1)
+    uint8_t* my_stage = stage_gen + (warp - 2) * (32 * 64);
     T* xg = reinterpret_cast<T*>(p.x);
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++t_use) {
+    TR_DECL
+    // this warp's share of tile ti's output accumulator: + b2, * gamma, + residual, staged coalesced store (in place)
+    auto drain_output = [&](int ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int ob = ti % K::OBUF;
       const int64_t m_warp = (int64_t)tile * FM + q * 32;
       const int64_t m = m_warp + lane;
-#pragma unroll 1
-      for (int j = 0; j < K::NCH; ++j) {
-        const int b = j & 1;
-        const uint32_t n_use = t_use * ((K::NCH + 1 - b) >> 1) + (j >> 1);
-        mbar_wait(smem_u32(s_full + b), n_use & 1);
-        tc_fence_after();
-        float v[32];
-        {
-          uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * FCH + s * 32, r);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(s_empty + b));
-        const float* bj = vec_b1 + j * FCH + s * 32;
-        uint4 pk[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bj + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bj + g * 8 + 4);
-          float* w = v + g * 8;
-          w[0] = gelu_fast(w[0] + b0.x); w[1] = gelu_fast(w[1] + b0.y);
-          w[2] = gelu_fast(w[2] + b0.z); w[3] = gelu_fast(w[3] + b0.w);
-          w[4] = gelu_fast(w[4] + b1.x); w[5] = gelu_fast(w[5] + b1.y);
-          w[6] = gelu_fast(w[6] + b1.z); w[7] = gelu_fast(w[7] + b1.w);
-          pk[g].x = pack2<T>(w[0], w[1]); pk[g].y = pack2<T>(w[2], w[3]);
-          pk[g].z = pack2<T>(w[4], w[5]); pk[g].w = pack2<T>(w[6], w[7]);
-        }
-        mbar_wait(smem_u32(h_empty + b), (n_use & 1) ^ 1);          // fc2 of the chunk that last used this buffer retired
-        uint8_t* hrow = h_gen + b * K::H_BYTES + s * FBLK + row * 64;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(hrow + ((g ^ sw) << 4)) = pk[g];
-        fence_async_smem();                                          // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(h_full + b));
-      }
-      // ---- output accumulator: + b2, * gamma, + residual, staged coalesced store (in place on x) ----
+      // ---- + b2, * gamma, + residual, staged coalesced store (in place on x) ----
       // the residual rows come from HBM: fetch them before blocking on the accumulator
       uint4 res[2][4];
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gq = 0; gq < 4; ++gq) {
           const int c = s + 4 * ci;
-          res[ci][g] = make_uint4(0, 0, 0, 0);
-          if (c < C / 32 && m < p.M) res[ci][g] = *reinterpret_cast<const uint4*>(xg + m * C + c * 32 + g * 8);
+          res[ci][gq] = make_uint4(0, 0, 0, 0);
+          if (c < C / 32 && m < p.M) res[ci][gq] = *reinterpret_cast<const uint4*>(xg + m * C + c * 32 + gq * 8);
         }
-      mbar_wait(smem_u32(o_full), o_use & 1);
+      TR_BEGIN
+      mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
+      TR_END(2)
       tc_fence_after();
-      ++o_use;
       if (s >= C / 32) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(o_empty));
+        if (lane == 0) mbar_arrive(smem_u32(o_empty + ob));
       }
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
@@ -319,7 +343,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         float v[32];
         {
           uint32_t r[32];
-          tc_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + c * 32, r);
+          tc_ld32(tmem_o + ob * C + ((uint32_t)(q * 32) << 16) + c * 32, r);
           tc_wait_ld();
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
@@ -327,18 +351,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         if (c + 4 >= C / 32) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(o_empty));
+          if (lane == 0) mbar_arrive(smem_u32(o_empty + ob));
         }
         const int n0 = c * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + g * 8;
-          float* w = v + g * 8;
+        for (int gq = 0; gq < 4; ++gq) {
+          const int n = n0 + gq * 8;
+          float* w = v + gq * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(vec_b2 + n), b1 = *reinterpret_cast<const float4*>(vec_b2 + n + 4);
           const float4 g0 = *reinterpret_cast<const float4*>(vec_g + n), g1 = *reinterpret_cast<const float4*>(vec_g + n + 4);
           float rr[8];
           {
-            const uint4 rq = res[ci][g];
+            const uint4 rq = res[ci][gq];
             float2 f;
             f = unpack2<T>(rq.x); rr[0] = f.x; rr[1] = f.y;
             f = unpack2<T>(rq.y); rr[2] = f.x; rr[3] = f.y;
@@ -352,7 +376,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           uint4 pk;
           pk.x = pack2<T>(w[0], w[1]); pk.y = pack2<T>(w[2], w[3]);
           pk.z = pack2<T>(w[4], w[5]); pk.w = pack2<T>(w[6], w[7]);
-          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4)) = pk;
         }
         __syncwarp();
         const int piece = lane & 3;
@@ -367,7 +391,58 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         }
         __syncwarp();
       }
+    };
+    int pending = -1;
+#pragma unroll 1
+    for (int g = grp; g < total; g += 2) {
+      const int ti = g / K::NCH, j = g - ti * K::NCH;
+      const int b = grp;
+      const uint32_t n_use = (uint32_t)(g >> 1);
+      TR_BEGIN
+      mbar_wait(smem_u32(s_full + b), n_use & 1);
+      TR_END(0)
+      tc_fence_after();
+#pragma unroll 1
+      for (int hk = 0; hk < 2; ++hk) {
+        const int kb = half * 2 + hk;        // K-block of the chunk = 32 hidden columns
+        float v[32];
+        {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * FCH + kb * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+        }
+        if (hk == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(s_empty + b));
+        }
+        const float* bj = vec_b1 + j * FCH + kb * 32;
+        uint4 pk[4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          pk[gq] = bias_gelu_pack8<T>(v + gq * 8, *reinterpret_cast<const float4*>(bj + gq * 8),
+                                      *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+        TR_BEGIN
+        if (hk == 0) mbar_wait(smem_u32(h_empty + b), (n_use & 1) ^ 1);   // fc2 that last read this buffer retired
+        TR_END(1)
+        uint8_t* hrow = h_gen + b * K::H_BYTES + kb * FBLK + row * 64;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(hrow + ((gq ^ sw) << 4)) = pk[gq];
+      }
+      fence_async_smem();                                          // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(h_full + b));
+
+      // The tile's output accumulator is complete only after the OTHER group's last chunk went through fc2, so this
+      // warp drains tile ti one chunk late (after its first chunk of the next tile) instead of idling on o_full.
+      if (pending >= 0) { drain_output(pending); pending = -1; }
+      if ((g + 2) / K::NCH != ti) pending = ti;       // that was this group's last chunk of tile ti
     }
+    if (pending >= 0) drain_output(pending);
+    if (lane == 0 && warp == 2) { TR_DUMP(16) }
+    if (lane == 0 && warp == 10) { TR_DUMP(24) }
   }
 
   tc_fence_before();
@@ -444,6 +519,15 @@ int launch_fused(int dtype, const void* y, const void* w1, const void* w2, const
 }
 
 }  // namespace
+
+int mlp_fused_trace(long long* out64) {
+#ifdef GCV_FUSED_TRACE
+  return cudaMemcpyFromSymbol(out64, gcv_fused_trace, 64 * sizeof(long long)) == cudaSuccess ? 64 : -1;
+#else
+  (void)out64;
+  return 0;
+#endif
+}
 
 bool mlp_fused_supported(int dtype, int C) { return (dtype == GCV_BF16 || dtype == GCV_F16) && (C == 96 || C == 192); }
 
