@@ -49,6 +49,7 @@ struct Params {
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
   int vec_smem;        // bias / gamma are staged in shared memory (N <= kVecMaxN)
+  int pair;            // 2-CTA cluster: the pair works on two M-tiles of the same N-tile and shares the B tile by TMA multicast
   int debug;           // profiling knob (GCV_DEBUG): 1 = epilogue skips all work, 2 = skips stores
   gcv_epilogue ep;
 };
@@ -75,7 +76,10 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
     if (n + e < N) epilogue_one<T>(ep, m, n + e, N, v[e], D);
 }
 
-template <typename T>
+// MODE: 0 = staged epilogue, general (bias / act / layer-scale / residual); 1 = staged, bias + GELU only (packed fp16
+// math); 2 = element-wise cold path (ragged / fp32 / reparameterisation outputs).  Separate instantiations keep each
+// epilogue within the 96 registers a 576-thread CTA leaves per thread.
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* D, const Params p) {
@@ -100,7 +104,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
-      mbar_init(smem_u32(empty_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), p.pair ? 2 : 1);     // pair mode: both CTAs' MMAs release a stage
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       mbar_init(smem_u32(tmem_full + s), 1);
@@ -123,23 +127,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t crank = p.pair ? cluster_ctarank() : 0;
+  // tile walk: a CTA (or a pair, sharing n_blk and taking m-tiles 2i, 2i+1) strides over the tile list
+  const int walker = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walkers = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int walk_tiles = p.pair ? ((p.tiles_m + 1) >> 1) * p.tiles_n : num_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      for (int tile = walker; tile < walk_tiles; tile += walkers) {
+        const int mw = tile / p.tiles_n, n_blk = tile - mw * p.tiles_n;
+        const int m_blk = p.pair ? 2 * mw + (int)crank : mw;        // may be one past the end: TMA zero-fills, nothing is stored
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = tiles_base + stage * stage_bytes;
           tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
-          tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
+          if (p.pair) {
+            // each CTA fetches half of the B tile and multicasts it into both CTAs' stage
+            const uint32_t half_rows = (uint32_t)p.block_n >> 1;
+            tma_load_2d_mcast(sa + a_bytes + crank * half_rows * (BK * 2), &tmap_b, fb, kb * BK,
+                              n_blk * p.block_n + (int)(crank * half_rows), (uint16_t)3);
+          } else {
+            tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -151,7 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = walker; tile < walk_tiles; tile += walkers) {
         mbar_wait(smem_u32(tmem_empty + as), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
@@ -166,7 +184,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint64_t bd = umma_desc(sa + a_bytes + k * 32);
             tc_mma(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
           }
-          tc_commit(smem_u32(empty_bar + stage));       // frees the smem stage once these MMAs retire
+          if (p.pair) tc_commit_mcast(smem_u32(empty_bar + stage), (uint16_t)3);   // the peer's TMA writes into this stage too
+          else tc_commit(smem_u32(empty_bar + stage));  // frees the smem stage once these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(smem_u32(tmem_full + as));             // accumulator complete
@@ -183,15 +202,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int quarter = warp & 3;                        // TMEM lane quarter this warp may read
     const int sub = ew >> 2;                             // the 4 warps of a quarter take chunks sub, sub+4, ...
     const int chunks = p.block_n / 32;
-    const bool vec_ok = p.vec_ok != 0;
-    // bias + GELU and nothing else (the ConvNeXt fc1 shape): packed-half epilogue
-    const bool gelu_only = vec_ok && p.vec_smem && p.ep.act == GCV_ACT_GELU && p.ep.bias && !p.ep.gamma && !p.ep.residual;
+    constexpr bool vec_ok = MODE != 2;
+    constexpr bool gelu_only = MODE == 1;
     uint8_t* my_stage = stage_base + ew * kStageWarp;
     const gcv_epilogue& ep = p.ep;
     int as = -1;
     uint32_t aphase = 1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+    for (int tile = walker; tile < walk_tiles; tile += walkers) {
+      const int mw = tile / p.tiles_n, n_blk = tile - mw * p.tiles_n;
+      const int m_blk = p.pair ? 2 * mw + (int)crank : mw;
       if (++as == p.acc_stages) as = 0;
       if (as == 0) aphase ^= 1;
       mbar_wait(smem_u32(tmem_full + as), aphase);
@@ -211,83 +230,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         continue;
       }
       for (int c = sub; c < chunks; c += 4) {
-        float v[32];
-        {
-          uint32_t r[32];
-          tc_ld32(t_row + c * 32, r);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        }
-        if (c + 4 >= chunks) {
-          tc_fence_before();                             // all TMEM reads of this tile by this warp are done:
-          __syncwarp();                                  // hand the accumulator stage back to the MMA warp early
-          if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
-        }
         const int n0 = n_blk * p.block_n + c * 32;
-        if (!vec_ok) {
-          if (m < p.M) {
+        // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 576-thread CTA
+        // leaves 96 registers per thread)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              epilogue_slow8<T>(ep, m, n0 + j * 8, p.N, v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3],
-                                v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7], D);
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          {
+            uint32_t r[16];
+            tc_ld16(t_row + c * 32 + h * 16, r);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
           }
-          continue;
-        }
-        // ---- phase A ----
+          if (h == 1 && c + 4 >= chunks) {
+            tc_fence_before();                           // all TMEM reads of this tile by this warp are done:
+            __syncwarp();                                // hand the accumulator stage back to the MMA warp early
+            if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+          }
+          if (!vec_ok) {
+            if (m < p.M) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + j * 8;
-          float* w = v + j * 8;
-          if (gelu_only && n + 8 <= p.N) {
-            // fc1 fast path: bias + GELU in packed fp16 arithmetic, done at pack time below
-          } else if (n + 8 <= p.N) {
-            if (p.vec_smem) {
-              if (ep.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n);
-                const float4 b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
-                w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
-                w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+              for (int j = 0; j < 2; ++j)
+                epilogue_slow8<T>(ep, m, n0 + h * 16 + j * 8, p.N, v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3],
+                                  v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7], D);
+            }
+            continue;
+          }
+          // ---- phase A ----
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = h * 2 + jj;
+            const int n = n0 + j * 8;
+            float* w = v + jj * 8;
+            uint4 q;
+            if (gelu_only && n + 8 <= p.N) {
+              // fc1 fast path: bias + GELU in packed fp16 arithmetic
+              q = bias_gelu_pack8<T>(w, *reinterpret_cast<const float4*>(vec_bias + n),
+                                     *reinterpret_cast<const float4*>(vec_bias + n + 4));
+            } else {
+              if (n + 8 <= p.N) {
+                if (p.vec_smem) {
+                  if (ep.bias) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n);
+                    const float4 b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
+                    w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+                    w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+                  }
+                } else if (ep.bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+                  w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+                  w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+                }
+                if (ep.act != GCV_ACT_NONE) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] = apply_act_fast(w[e], ep.act);
+                }
+                if (ep.gamma) {
+                  const float4 g0 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n)
+                                               : __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+                  const float4 g1 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n + 4)
+                                               : __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
+                  w[0] *= g0.x; w[1] *= g0.y; w[2] *= g0.z; w[3] *= g0.w;
+                  w[4] *= g1.x; w[5] *= g1.y; w[6] *= g1.z; w[7] *= g1.w;
+                }
+                if (ep.residual && m < p.M) {
+                  float rr[8];
+                  load8<T>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + n, rr);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w[e] += rr[e];
+                }
+              } else {
+                // ragged right edge (N % 8 != 0): finish these columns element-wise, nothing staged
+                if (m < p.M && n < p.N)
+                  epilogue_slow8<T>(ep, m, n, p.N, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], D);
               }
-            } else if (ep.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-              w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
-              w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+              q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
+              q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
             }
-            if (ep.act != GCV_ACT_NONE) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[e] = apply_act_fast(w[e], ep.act);
-            }
-            if (ep.gamma) {
-              const float4 g0 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n)
-                                           : __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
-              const float4 g1 = p.vec_smem ? *reinterpret_cast<const float4*>(vec_gamma + n + 4)
-                                           : __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4));
-              w[0] *= g0.x; w[1] *= g0.y; w[2] *= g0.z; w[3] *= g0.w;
-              w[4] *= g1.x; w[5] *= g1.y; w[6] *= g1.z; w[7] *= g1.w;
-            }
-            if (ep.residual && m < p.M) {
-              float rr[8];
-              load8<T>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + n, rr);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[e] += rr[e];
-            }
-          } else {
-            // ragged right edge (N % 8 != 0): finish these columns element-wise, nothing staged
-            if (m < p.M && n < p.N)
-              epilogue_slow8<T>(ep, m, n, p.N, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], D);
+            *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
           }
-          uint4 q;
-          if (gelu_only && n + 8 <= p.N) {
-            q = bias_gelu_pack8<T>(v + j * 8, *reinterpret_cast<const float4*>(vec_bias + n),
-                                   *reinterpret_cast<const float4*>(vec_bias + n + 4));
-          } else {
-            q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
-            q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
-          }
-          *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
         }
+        if (!vec_ok) continue;
         __syncwarp();
         if (p.debug == 2) { __syncwarp(); continue; }
         // ---- phase B ----
@@ -322,6 +347,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();       // the peer may still be multicasting into / arriving on this CTA's smem
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -400,7 +426,6 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
               (long long)K, (long long)lda, (long long)ldb);
   GCV_REQUIRE(M > 0 && N > 0 && N < (1 << 30), "bad GEMM shape");
   static int sms = 0;
-  static bool attr_set[2] = {false, false};
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -440,28 +465,63 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dtype, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map(&mb, dtype, B, N, K, ldb, p.block_n);
+  // pair mode (opt-in, GCV_GEMM_PAIR=1): two CTAs on neighbouring M-tiles of one N-tile fetch half of the B tile each
+  // and multicast it.  Correct (tests cover it) but measured no faster on B200: at cluster size 2 the L2 already
+  // de-duplicates the two unicast requests, and the 128x256 single-CTA tile is shared-memory-bandwidth bound.
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("GCV_GEMM_PAIR"); pair_env = e ? atoi(e) : 0; }
+    p.pair = (pair_env && p.tiles_m >= 2 && K >= 256 && p.block_n >= 128 && (int64_t)p.tiles_m * p.tiles_n >= 2 * sms) ? 1 : 0;
+  }
+  rc = make_map(&mb, dtype, B, N, K, ldb, p.pair ? p.block_n / 2 : p.block_n);
   if (rc) return rc;
 
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  const int ti = dtype == GCV_BF16 ? 0 : 1;
-  if (!attr_set[ti]) {
-    cudaError_t e = dtype == GCV_BF16
-                        ? cudaFuncSetAttribute(gemm_tcgen05_kernel<__nv_bfloat16>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)
-                        : cudaFuncSetAttribute(gemm_tcgen05_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               kDynSmem);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", kDynSmem, cudaGetErrorString(e));
-      return GCV_ERR_CUDA;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  if (p.pair) grid &= ~1;
+  const int mode = !p.vec_ok ? 2
+                   : (p.vec_smem && ep->act == GCV_ACT_GELU && ep->bias && !ep->gamma && !ep->residual) ? 1 : 0;
+  cudaError_t le = cudaSuccess;
+  static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
+  bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode];
+  auto launch = [&](auto kernel) {
+    if (!attr_done) {
+      le = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
+      if (le != cudaSuccess) return;
+      attr_done = true;
     }
-    attr_set[ti] = true;
+    if (!p.pair) {
+      kernel<<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
+      le = cudaGetLastError();
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = kDynSmem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, D, p);
+    }
+  };
+  if (dtype == GCV_BF16) {
+    if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0>);
+    else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1>);
+    else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2>);
+  } else {
+    if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0>);
+    else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1>);
+    else launch(gemm_tcgen05_kernel<__half, 2>);
   }
-  if (dtype == GCV_BF16)
-    gemm_tcgen05_kernel<__nv_bfloat16><<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
-  else
-    gemm_tcgen05_kernel<__half><<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
+  if (le != cudaSuccess) {
+    set_error("gemm_tcgen05 launch: %s", cudaGetErrorString(le));
+    return GCV_ERR_CUDA;
+  }
   return check_launch("gemm_tcgen05");
 }
 

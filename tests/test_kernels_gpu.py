@@ -71,6 +71,22 @@ def test_gemm_tcgen05_many_tiles_persistent():
     _close(d, a.float() @ b.float().t(), 1e-2, "persistent")
 
 
+@pytest.mark.parametrize("shape", [(40000, 512, 512), (148 * 128 * 2 + 128 * 3 + 5, 384, 1536), (20000, 1536, 384)])
+def test_gemm_tcgen05_pair_mode_multicast(shape, monkeypatch):
+    """Opt-in pair mode: 2-CTA clusters that share the B tile by TMA multicast (odd M-tile counts included).
+    GCV_GEMM_PAIR is read once per process, so this test is only meaningful when it runs with the variable set
+    (tools/run_pair_tests.sh); otherwise it exercises the default path on the same shapes."""
+    L = _lib()
+    M, N, K = shape
+    a, b = _rand(M, K, dtype=torch.bfloat16, seed=7), _rand(N, K, dtype=torch.bfloat16, seed=8, scale=K ** -0.5)
+    bias = _rand(N, seed=9)
+    res = _rand(M, N, dtype=torch.bfloat16, seed=10)
+    want = res.float() + (a.float() @ b.float().t() + bias)
+    L.gemm(a, b, res, M, N, K, bias=bias, residual=res, ldr=N, backend=L.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    _close(res, want, 1e-2, f"pair {shape}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("backend", ["simt", "auto"])
 def test_gemm_epilogues(dtype, backend):
