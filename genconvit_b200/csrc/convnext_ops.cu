@@ -496,28 +496,37 @@ int ln_dispatch(int C, F&& f) {
 }
 
 // Stem im2col (4x4 stride 4, 3 channels): row (b,ho,wo), column (kh*4+kw)*3 + c.
+// One thread per output row: 12 independent 16-byte loads in flight (a warp reads 512 contiguous bytes per
+// (channel, kh) image row) and one contiguous 48-element row out (six 16-byte stores for 16-bit T).
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_patchify_nchw_kernel(const float* __restrict__ x, T* __restrict__ a, int B, int H, int W) {
   const int Ho = H / 4, Wo = W / 4;
-  // one thread per (b, ho, kh, wo): reads 3 x float4 (coalesced along wo), writes 12 contiguous elements
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Ho * 4 * Wo;
+  const int64_t total = (int64_t)B * Ho * Wo;
   if (idx >= total) return;
   const int wo = (int)(idx % Wo);
-  int64_t t = idx / Wo;
-  const int kh = (int)(t & 3); t >>= 2;
+  const int64_t t = idx / Wo;
   const int ho = (int)(t % Ho);
   const int64_t b = t / Ho;
-  float4 px[3];
+  float4 px[4][3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-    px[c] = *reinterpret_cast<const float4*>(x + ((b * 3 + c) * H + (ho * 4 + kh)) * (int64_t)W + wo * 4);
-  T* dst = a + ((b * Ho + ho) * Wo + wo) * 48 + kh * 12;
-  const float v[12] = {px[0].x, px[1].x, px[2].x, px[0].y, px[1].y, px[2].y,
-                       px[0].z, px[1].z, px[2].z, px[0].w, px[1].w, px[2].w};
+  for (int kh = 0; kh < 4; ++kh)
 #pragma unroll
-  for (int i = 0; i < 12; ++i) dst[i] = from_f<T>(v[i]);
+    for (int c = 0; c < 3; ++c)
+      px[kh][c] = __ldg(reinterpret_cast<const float4*>(x + ((b * 3 + c) * H + (ho * 4 + kh)) * (int64_t)W + wo * 4));
+  float v[48];
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh) {
+    float* o = v + kh * 12;
+    o[0] = px[kh][0].x; o[1] = px[kh][1].x; o[2] = px[kh][2].x;
+    o[3] = px[kh][0].y; o[4] = px[kh][1].y; o[5] = px[kh][2].y;
+    o[6] = px[kh][0].z; o[7] = px[kh][1].z; o[8] = px[kh][2].z;
+    o[9] = px[kh][0].w; o[10] = px[kh][1].w; o[11] = px[kh][2].w;
+  }
+  T* dst = a + idx * 48;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) store8<T>(dst + i * 8, v + i * 8);
 }
 
 template <typename T>
@@ -525,17 +534,35 @@ __global__ void __launch_bounds__(256)
 stem_patchify_nhwc_kernel(const T* __restrict__ x, T* __restrict__ a, int B, int H, int W) {
   const int Ho = H / 4, Wo = W / 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Ho * 4 * Wo;
+  const int64_t total = (int64_t)B * Ho * Wo;
   if (idx >= total) return;
   const int wo = (int)(idx % Wo);
-  int64_t t = idx / Wo;
-  const int kh = (int)(t & 3); t >>= 2;
+  const int64_t t = idx / Wo;
   const int ho = (int)(t % Ho);
   const int64_t b = t / Ho;
-  const T* src = x + ((b * H + ho * 4 + kh) * (int64_t)W + wo * 4) * 3;
-  T* dst = a + ((b * Ho + ho) * Wo + wo) * 48 + kh * 12;
+  T* dst = a + idx * 48;
+  if constexpr (sizeof(T) == 2) {
+    // a 4-pixel x 3-channel run is 24 contiguous bytes (8-byte aligned): 3 x 8-byte loads per image row
+    uint2 r[4][3];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) dst[i] = src[i];
+    for (int kh = 0; kh < 4; ++kh) {
+      const uint2* src = reinterpret_cast<const uint2*>(x + ((b * H + ho * 4 + kh) * (int64_t)W + wo * 4) * 3);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[kh][i] = __ldg(src + i);
+    }
+    uint2* d2 = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) d2[kh * 3 + i] = r[kh][i];
+  } else {
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+      const T* src = x + ((b * H + ho * 4 + kh) * (int64_t)W + wo * 4) * 3;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) dst[kh * 12 + i] = src[i];
+    }
+  }
 }
 
 // Global average pool over HW then LayerNorm over C: one CTA per image, thread per channel (strided).
@@ -701,7 +728,7 @@ int ln_patchify2(int dtype, const void* x, void* a, const float* w, const float*
 
 int stem_patchify(int dtype, bool nchw, const void* x, void* a, int B, int H, int W, cudaStream_t stream) {
   GCV_REQUIRE(H % 4 == 0 && W % 4 == 0, "stem_patchify: H, W must be multiples of 4");
-  const int64_t total = (int64_t)B * (H / 4) * 4 * (W / 4);
+  const int64_t total = (int64_t)B * (H / 4) * (W / 4);
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     const unsigned grid = (unsigned)((total + 255) / 256);

@@ -49,7 +49,6 @@ struct Params {
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
   int vec_smem;        // bias / gamma are staged in shared memory (N <= kVecMaxN)
-  int pair;            // 2-CTA cluster: the pair works on two M-tiles of the same N-tile and shares the B tile by TMA multicast
   int debug;           // profiling knob (GCV_DEBUG): 1 = epilogue skips all work, 2 = skips stores
   gcv_epilogue ep;
 };
@@ -79,7 +78,11 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
 // MODE: 0 = staged epilogue, general (bias / act / layer-scale / residual); 1 = staged, bias + GELU only (packed fp16
 // math); 2 = element-wise cold path (ragged / fp32 / reparameterisation outputs).  Separate instantiations keep each
 // epilogue within the 96 registers a 576-thread CTA leaves per thread.
-template <typename T, int MODE>
+// DUO: the CTA pair of a 2-CTA cluster computes one 256 x block_n tile with cta_group::2 MMAs: each CTA stages its
+// own 128 rows of A and HALF of the B tile (so a stage is 16 KB + block_n/2 x 128 B instead of 16 KB + block_n x 128 B:
+// one third less shared-memory and L2 traffic per MAC, deeper pipeline), the leader CTA issues the MMAs, and each
+// CTA drains its own 128 accumulator rows from its own TMEM.
+template <typename T, int MODE, bool DUO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* D, const Params p) {
@@ -96,7 +99,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)p.block_n * BK * 2;
+  const uint32_t b_rows = DUO ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;     // B rows staged by this CTA
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = b_rows * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -104,19 +108,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
-      mbar_init(smem_u32(empty_bar + s), p.pair ? 2 : 1);     // pair mode: both CTAs' MMAs release a stage
+      mbar_init(smem_u32(empty_bar + s), 1);
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       mbar_init(smem_u32(tmem_full + s), 1);
-      mbar_init(smem_u32(tmem_empty + s), kEpiWarps);
+      mbar_init(smem_u32(tmem_empty + s), DUO ? 2 * kEpiWarps : kEpiWarps);   // DUO: both CTAs' epilogues release the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (DUO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (p.vec_smem) {
     // bias / layer-scale vectors are read by every epilogue thread for every tile: keep them on chip
@@ -127,14 +138,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (p.pair) cluster_sync_all();
+  if constexpr (DUO) cluster_sync_all();     // barrier inits / TMEM allocation of both CTAs visible before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  const uint32_t crank = p.pair ? cluster_ctarank() : 0;
-  // tile walk: a CTA (or a pair, sharing n_blk and taking m-tiles 2i, 2i+1) strides over the tile list
-  const int walker = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int walkers = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int walk_tiles = p.pair ? ((p.tiles_m + 1) >> 1) * p.tiles_n : num_tiles;
+  const uint32_t crank = DUO ? cluster_ctarank() : 0;
+  const bool leader = crank == 0;
+  // tile walk: a CTA (or a pair, taking m-tiles 2i and 2i+1 of one n-tile) strides over the tile list
+  const int walker = DUO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walkers = DUO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int walk_tiles = DUO ? ((p.tiles_m + 1) >> 1) * p.tiles_n : num_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -143,19 +155,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int tile = walker; tile < walk_tiles; tile += walkers) {
         const int mw = tile / p.tiles_n, n_blk = tile - mw * p.tiles_n;
-        const int m_blk = p.pair ? 2 * mw + (int)crank : mw;        // may be one past the end: TMA zero-fills, nothing is stored
+        const int m_blk = DUO ? 2 * mw + (int)crank : mw;           // may be one past the end: TMA zero-fills, nothing is stored
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
-          mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = tiles_base + stage * stage_bytes;
-          tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
-          if (p.pair) {
-            // each CTA fetches half of the B tile and multicasts it into both CTAs' stage
-            const uint32_t half_rows = (uint32_t)p.block_n >> 1;
-            tma_load_2d_mcast(sa + a_bytes + crank * half_rows * (BK * 2), &tmap_b, fb, kb * BK,
-                              n_blk * p.block_n + (int)(crank * half_rows), (uint16_t)3);
+          if constexpr (DUO) {
+            // both CTAs' loads complete on the leader's barrier, which therefore expects two stages' worth of bytes
+            if (leader) mbar_expect_tx(fb, 2 * stage_bytes);
+            tma_load_2d_2sm(sa, &tmap_a, fb, kb * BK, m_blk * BM);
+            tma_load_2d_2sm(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n + (int)(crank * b_rows));
           } else {
+            mbar_expect_tx(fb, stage_bytes);
+            tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
             tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -164,7 +176,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && (!DUO || leader)) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -182,13 +194,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int k = 0; k < kmma; ++k) {
             const uint64_t ad = umma_desc(sa + k * 32);
             const uint64_t bd = umma_desc(sa + a_bytes + k * 32);
-            tc_mma(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
+            if constexpr (DUO) tc_mma_2sm(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
+            else tc_mma(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
           }
-          if (p.pair) tc_commit_mcast(smem_u32(empty_bar + stage), (uint16_t)3);   // the peer's TMA writes into this stage too
+          if constexpr (DUO) tc_commit_2sm(smem_u32(empty_bar + stage));   // frees this stage in both CTAs
           else tc_commit(smem_u32(empty_bar + stage));  // frees the smem stage once these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(smem_u32(tmem_full + as));             // accumulator complete
+        if constexpr (DUO) tc_commit_2sm(smem_u32(tmem_full + as));      // accumulator complete, in both CTAs' TMEM
+        else tc_commit(smem_u32(tmem_full + as));        // accumulator complete
         if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
@@ -206,11 +220,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr bool gelu_only = MODE == 1;
     uint8_t* my_stage = stage_base + ew * kStageWarp;
     const gcv_epilogue& ep = p.ep;
+    // hand an accumulator stage back to the MMA warp (DUO: the leader CTA's, from either CTA)
+    auto release_acc = [&](int a) {
+      if (DUO && !leader) mbar_arrive_remote(smem_u32(tmem_empty + a), 0);
+      else mbar_arrive(smem_u32(tmem_empty + a));
+    };
     int as = -1;
     uint32_t aphase = 1;
     for (int tile = walker; tile < walk_tiles; tile += walkers) {
       const int mw = tile / p.tiles_n, n_blk = tile - mw * p.tiles_n;
-      const int m_blk = p.pair ? 2 * mw + (int)crank : mw;
+      const int m_blk = DUO ? 2 * mw + (int)crank : mw;
       if (++as == p.acc_stages) as = 0;
       if (as == 0) aphase ^= 1;
       mbar_wait(smem_u32(tmem_full + as), aphase);
@@ -221,12 +240,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (sub >= chunks) {                               // narrow tile: this warp has no chunk, release immediately
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+        if (lane == 0) release_acc(as);
       }
       if (p.debug == 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0 && sub < chunks) mbar_arrive(smem_u32(tmem_empty + as));
+        if (lane == 0 && sub < chunks) release_acc(as);
         continue;
       }
       for (int c = sub; c < chunks; c += 4) {
@@ -246,7 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (h == 1 && c + 4 >= chunks) {
             tc_fence_before();                           // all TMEM reads of this tile by this warp are done:
             __syncwarp();                                // hand the accumulator stage back to the MMA warp early
-            if (lane == 0) mbar_arrive(smem_u32(tmem_empty + as));
+            if (lane == 0) release_acc(as);
           }
           if (!vec_ok) {
             if (m < p.M) {
@@ -347,9 +366,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (p.pair) cluster_sync_all();       // the peer may still be multicasting into / arriving on this CTA's smem
+  if constexpr (DUO) cluster_sync_all();   // the peer may still be signalling this CTA's barriers / reading its smem
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (DUO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -435,16 +457,19 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   p.M = M; p.N = (int)N; p.K = (int)K;
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, (int)N, sms);
   GCV_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "block_n must be a multiple of 32 in [32,256]");
-  const int stage_bytes = BM * BK * 2 + p.block_n * BK * 2;
+  p.tiles_m = (int)((M + BM - 1) / BM);
+  p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
+  // DUO (cta_group::2 pairs) for the large contractions: they are shared-memory / L2 bandwidth bound with one CTA per
+  // 128 x block_n tile.  GCV_GEMM_DUO=0 disables it (A/B timing).
+  static int duo_env = -1;
+  if (duo_env < 0) { const char* e = getenv("GCV_GEMM_DUO"); duo_env = e ? atoi(e) : 1; }
+  const bool duo = duo_env && p.tiles_m >= 2 && K >= 256 && p.block_n >= 64 && (int64_t)p.tiles_m * p.tiles_n >= 2 * sms;
+  const int stage_bytes = BM * BK * 2 + (duo ? p.block_n / 2 : p.block_n) * BK * 2;
   p.acc_stages = 512 / p.block_n;
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
   p.num_stages = kTileSmem / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-  p.tiles_m = (int)((M + BM - 1) / BM);
-  p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
-  const uint32_t fmt = dtype == GCV_BF16 ? 1u : 0u;
-  // cute::UMMA::InstrDescriptor: c_format F32 [4,6), a/b format [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  p.idesc = umma_idesc_f16(dtype == GCV_BF16, duo ? 2 * BM : BM, p.block_n);
   p.ep = *ep;
   {
     static int dbg = -1;
@@ -465,32 +490,24 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dtype, A, M, K, lda, BM);
   if (rc) return rc;
-  // pair mode (opt-in, GCV_GEMM_PAIR=1): two CTAs on neighbouring M-tiles of one N-tile fetch half of the B tile each
-  // and multicast it.  Correct (tests cover it) but measured no faster on B200: at cluster size 2 the L2 already
-  // de-duplicates the two unicast requests, and the 128x256 single-CTA tile is shared-memory-bandwidth bound.
-  {
-    static int pair_env = -1;
-    if (pair_env < 0) { const char* e = getenv("GCV_GEMM_PAIR"); pair_env = e ? atoi(e) : 0; }
-    p.pair = (pair_env && p.tiles_m >= 2 && K >= 256 && p.block_n >= 128 && (int64_t)p.tiles_m * p.tiles_n >= 2 * sms) ? 1 : 0;
-  }
-  rc = make_map(&mb, dtype, B, N, K, ldb, p.pair ? p.block_n / 2 : p.block_n);
+  rc = make_map(&mb, dtype, B, N, K, ldb, duo ? p.block_n / 2 : p.block_n);
   if (rc) return rc;
 
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);
-  if (p.pair) grid &= ~1;
+  if (duo) grid &= ~1;
   const int mode = !p.vec_ok ? 2
                    : (p.vec_smem && ep->act == GCV_ACT_GELU && ep->bias && !ep->gamma && !ep->residual) ? 1 : 0;
   cudaError_t le = cudaSuccess;
-  static bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
-  bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode];
+  static bool attr_set[2][3][2] = {};
+  bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode][duo ? 1 : 0];
   auto launch = [&](auto kernel) {
     if (!attr_done) {
       le = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
       if (le != cudaSuccess) return;
       attr_done = true;
     }
-    if (!p.pair) {
+    if (!duo) {
       kernel<<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
       le = cudaGetLastError();
     } else {
@@ -510,13 +527,25 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
     }
   };
   if (dtype == GCV_BF16) {
-    if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0>);
-    else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1>);
-    else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2>);
+    if (duo) {
+      if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, true>);
+      else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, true>);
+      else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, true>);
+    } else {
+      if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, false>);
+      else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, false>);
+      else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, false>);
+    }
   } else {
-    if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0>);
-    else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1>);
-    else launch(gemm_tcgen05_kernel<__half, 2>);
+    if (duo) {
+      if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, true>);
+      else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, true>);
+      else launch(gemm_tcgen05_kernel<__half, 2, true>);
+    } else {
+      if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, false>);
+      else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, false>);
+      else launch(gemm_tcgen05_kernel<__half, 2, false>);
+    }
   }
   if (le != cudaSuccess) {
     set_error("gemm_tcgen05 launch: %s", cudaGetErrorString(le));
