@@ -360,7 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16", "fp32"],
+                    help="kernel precision; fp16 is BASELINE config 2 (the reference's own --fp16 mode); bf16 runs at the same speed")
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--fpv", type=int, default=16, help="frames per video")
     ap.add_argument("--no-graph", action="store_true")
