@@ -3,6 +3,7 @@
 // timm==0.6.5 ConvNeXt as reached from reference model/genconvit_ed.py:68,
 // model/genconvit_vae.py:97 (arithmetic restated in oracle/backbones.py).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -623,9 +624,31 @@ int dispatch(int dtype, F&& f) {
 
 }  // namespace
 
+bool dwconv7_mma_supported(int dtype, int C);
+int dwconv7_mma(int dtype, const void* x, void* y, const float* taps, const float* bias, int B, int H, int W, int C,
+                cudaStream_t stream);
+int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
+                   cudaStream_t stream);
+
+// GCV_DWCONV=ffma keeps the 16-bit modes on the CUDA-core kernels (A/B timing); fp32 always runs there
+static bool dw_use_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCV_DWCONV");
+    v = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
                const float* ln_b, float eps, int B, int H, int W, int C, cudaStream_t stream) {
   GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
+  if (dw_use_mma() && dwconv7_mma_supported(dtype, C) && C % 8 == 0 && C <= 2048) {
+    // 16-bit modes: tensor-core depthwise conv (dwconv_mma.cu) into y, then the row LayerNorm in place
+    const int rc = dwconv7_mma(dtype, x, y, taps, bias, B, H, W, C, stream);
+    if (rc != GCV_OK) return rc;
+    return layernorm_rows(dtype, y, y, ln_w, ln_b, eps, (int64_t)B * H * W, C, stream);
+  }
   const int groups = (H + 6) / 7;
   const bool col_shape = (C == 96 || C == 192 || C == 384 || C == 768) && groups * (C / 2) <= 384;
   const size_t es = dtype == GCV_F32 ? 4 : 2;

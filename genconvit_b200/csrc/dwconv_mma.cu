@@ -1,0 +1,332 @@
+// Depthwise 7x7 convolution (pad 3, + bias) on the tensor cores, 16-bit activations, NHWC.
+// timm==0.6.5 ConvNeXtBlock.conv_dw as reached from reference model/genconvit_ed.py:68,
+// model/genconvit_vae.py:97 (arithmetic restated in oracle/backbones.py).
+//
+// A depthwise convolution has no contraction over channels, so the usual implicit GEMM does not
+// exist; on CUDA cores it costs 49 FMAs per output and is instruction-issue bound (the FFMA2
+// column kernel in convnext_ops.cu sits at 35 % of the FMA roof).  Here every channel is treated
+// as its own small banded problem instead: for one image row and one channel,
+//     out[y][x0 + n] = sum_dy  in[y + dy - 3][x0 - 3 + k] * T_dy[k][n],   T_dy[k][n] = w[dy][k - n]
+// with T_dy a 16 x 8 banded Toeplitz matrix (7 non-zero diagonals).  Stacking 16 images in the M
+// dimension gives a dense m16n8k16 tensor-core MMA per (channel, dy): 7/16 of its MACs are useful,
+// which is still ~6x fewer issued instructions per output than FFMA2, and the fp32 accumulation is
+// exact for 16-bit inputs.  One warp owns one channel pair (a 32-bit shared-memory word holds
+// both channels of a pixel) and marches down the image: each input row's A fragments are loaded
+// once and feed the 7 output rows in flight (7 x 2 MMAs), so all data reuse happens in registers.
+//
+// CTA = 16 warps = one 32-channel chunk of a (16 images x 8 output columns) tile, all rows.
+// Input rows arrive through a TMA ring (box = 32 ch x 17 px x 1 row x 16 images, 64B-swizzled;
+// out-of-image rows/columns/images are zero-filled by TMA, which is the conv padding).  Finished
+// output rows go through a padded shared-memory tile so that global stores are 16 bytes per lane
+// and 64 contiguous bytes per pixel.  The taps are rounded to the activation type (like every
+// other weight of the 16-bit modes); LayerNorm runs as a separate row pass over the stored result.
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace gcv {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn mma_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+constexpr int MM_IMGS = 16;                 // M rows of the MMA = images
+constexpr int MM_XOUT = 8;                  // N = output columns per tile
+constexpr int MM_XIN = 17;                  // staged input columns per tile (16 used; 17 spreads the swizzle phase)
+constexpr int MM_CCH = 32;                  // channels per CTA pass = 16 warps x 2
+constexpr int MM_THREADS = 512;
+constexpr uint32_t MM_SLOT_BYTES = MM_IMGS * MM_XIN * MM_CCH * 2;      // 17408 = 17 KiB (keeps slots 1024-aligned)
+constexpr int MM_STAGE_STRIDE = 17;         // words per staged output pixel (16 + 1 pad: conflict-light both ways)
+constexpr uint32_t MM_STAGE_BYTES = MM_IMGS * MM_XOUT * MM_STAGE_STRIDE * 4;   // 8704
+constexpr int MM_DEPTH = 8;                 // TMA ring slots (power of two)
+
+__device__ __forceinline__ void mm_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (std::is_same<T, __half>::value)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CTA b works on channel chunk b % n_chunks for the whole launch (its Toeplitz fragments are loaded once) and walks
+// the (image group, column tile) tiles b / n_chunks + i * (gridDim / n_chunks): the CTAs that run side by side cover
+// all chunks of the same pixels, so DRAM and L2 see whole pixels rather than 64 of every 2C bytes.
+// Pipeline step n of a CTA = input row (n % H) of its (n / H)-th tile.  The loop body is kept to ~70 instructions per
+// warp and step (the first version spent 400, mostly index arithmetic, and was issue-bound on exactly that).
+template <typename T>
+__device__ __forceinline__ void mma16816_init(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c) {
+  if constexpr (std::is_same<T, __half>::value)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, const float* __restrict__ taps,
+                   const float* __restrict__ bias, int B, int H, int W, int C, int xtiles, int n_tiles,
+                   int n_chunks) {
+  extern __shared__ uint8_t msm_dyn[];
+  // layout (1024-aligned so that the swizzle phase of a slot starts at 0): [ring 8 x 17408][stage 2 x 8704][full barriers]
+  uint8_t* msm_raw = msm_dyn + ((1024u - ((uint32_t)__cvta_generic_to_shared(msm_dyn) & 1023u)) & 1023u);
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(msm_raw);
+  const uint32_t stage_s = smem_base + MM_DEPTH * MM_SLOT_BYTES;
+  const uint32_t bar_s = stage_s + 2 * MM_STAGE_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cc = (int)blockIdx.x % n_chunks, tile0 = (int)blockIdx.x / n_chunks, tile_step = (int)gridDim.x / n_chunks;
+  const int my_subs = tile0 < n_tiles ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+  const int total_steps = my_subs * H;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MM_DEPTH; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8 * i), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer state (thread 0 only; kept in shared memory to save registers in the other 511 threads): the next
+  // pipeline step to fetch and where it lies
+  int* pst = reinterpret_cast<int*>(msm_raw + MM_DEPTH * MM_SLOT_BYTES + 2 * MM_STAGE_BYTES + 8 * MM_DEPTH);
+  if (threadIdx.x == 0) {
+    pst[0] = 0; pst[1] = 0; pst[2] = tile0; pst[3] = (tile0 % xtiles) * MM_XOUT - 3; pst[4] = (tile0 / xtiles) * MM_IMGS;
+  }
+  auto issue_next = [&]() {
+    int p_n = pst[0], p_yin = pst[1], p_tile = pst[2];
+    const int p_x = pst[3], p_b = pst[4];
+    if (p_n >= total_steps) return;
+    const uint32_t fb = bar_s + 8 * (p_n & (MM_DEPTH - 1));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(MM_SLOT_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_base + (p_n & (MM_DEPTH - 1)) * MM_SLOT_BYTES), "l"(reinterpret_cast<uint64_t>(&tm_x)), "r"(fb),
+          "r"(cc * MM_CCH), "r"(p_x), "r"(p_yin), "r"(p_b)
+        : "memory");
+    pst[0] = p_n + 1;
+    if (++p_yin == H) {
+      p_yin = 0;
+      p_tile += tile_step;
+      pst[2] = p_tile;
+      pst[3] = (p_tile % xtiles) * MM_XOUT - 3;
+      pst[4] = (p_tile / xtiles) * MM_IMGS;
+    }
+    pst[1] = p_yin;
+  };
+  if (threadIdx.x == 0)
+    for (int k = 0; k < MM_DEPTH; ++k) issue_next();
+
+  // A-fragment byte offsets inside a ring slot (64B swizzle: byte-address bits 4-5 ^= bits 7-8):
+  // index r*4 + q: image g + 8r, input column 2t + {0, 1, 8, 9}[q]
+  uint32_t aoff[8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 2 * t + (q & 1) + ((q >> 1) << 3);
+      const uint32_t lin = (uint32_t)(((g + 8 * r) * MM_XIN + k) * (MM_CCH * 2) + warp * 4);
+      aoff[r * 4 + q] = smem_base + (lin ^ (((lin >> 7) & 3u) << 4));
+    }
+  // output staging: this lane's accumulators are pixels (image g / g+8, column 2t / 2t+1) of channel pair `warp`;
+  // read-back role: thread i -> staged pixel i >> 2, channels 8*(i & 3) .. +7 of the chunk
+  uint32_t st_s = stage_s + 4u * (uint32_t)((g * MM_XOUT + 2 * t) * MM_STAGE_STRIDE + warp);
+  const int rb_px = threadIdx.x >> 2, rb_q = threadIdx.x & 3;
+  uint32_t rb_s = stage_s + 4u * (uint32_t)(rb_px * MM_STAGE_STRIDE + 4 * rb_q);
+
+  const int c0 = cc * MM_CCH + 2 * warp;
+  // Toeplitz B fragments: b[h] holds T_dy[k = 2t + 8h + {0,1}][n = g] = w[dy][k - n] (zero off the band)
+  uint32_t bfrag[2][7][2];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int dx0 = 2 * t + 8 * h - g;
+        const float v0 = (dx0 >= 0 && dx0 <= 6) ? __ldg(taps + (dy * 7 + dx0) * C + c0 + ch) : 0.0f;
+        const float v1 = (dx0 + 1 >= 0 && dx0 + 1 <= 6) ? __ldg(taps + (dy * 7 + dx0 + 1) * C + c0 + ch) : 0.0f;
+        bfrag[ch][dy][h] = pack2<T>(v0, v1);
+      }
+  const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + c0));
+
+  // The words of pipeline step n are fetched from the ring one step ahead, so their shared-memory latency and bank
+  // conflicts overlap the previous step's MMAs.
+  int n = 0;
+  uint32_t wn[8];
+  auto prefetch = [&](int nn) {
+    if (nn < total_steps) {
+      const uint32_t slot = (uint32_t)nn & (MM_DEPTH - 1);
+      mm_mbar_wait(bar_s + 8 * slot, ((uint32_t)nn / MM_DEPTH) & 1u);
+      const uint32_t so = slot * MM_SLOT_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wn[j]) : "r"(aoff[j] + so));
+    }
+  };
+  prefetch(0);
+
+  uint32_t stg_flip = MM_STAGE_BYTES;
+  const uint32_t row_bytes = (uint32_t)W * (uint32_t)C * 2u;
+  const int nsteps7 = ((H + 6 + 6) / 7) * 7;   // H + 6 steps, rounded up to whole turns of the 7-slot accumulator ring
+  for (int i = 0; i < my_subs; ++i) {
+    const int tile = tile0 + i * tile_step;
+    const int ig = tile / xtiles, xt = tile - ig * xtiles;
+    const int rb_b = ig * MM_IMGS + (rb_px >> 3), rb_x = xt * MM_XOUT + (rb_px & 7);
+    const bool rb_ok = rb_b < B && rb_x < W;
+    uint32_t rb_off = ((uint32_t)(rb_b * H) * (uint32_t)W + (uint32_t)rb_x) * (uint32_t)(C * 2) + (uint32_t)(cc * MM_CCH + 8 * rb_q) * 2u;   // output row 0
+
+    float acc[7][2][4];                        // [output-row slot][channel][fragment]
+    // rows 0..2 never see a dy = 0 tap (their first input row is row 0), so they start from the bias here; every
+    // other output row is initialised by its dy = 0 MMA (C operand = bias)
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      acc[sl][0][0] = acc[sl][0][1] = acc[sl][0][2] = acc[sl][0][3] = bv.x;
+      acc[sl][1][0] = acc[sl][1][1] = acc[sl][1][2] = acc[sl][1][3] = bv.y;
+    }
+    // step s consumes input row s - 3 (when inside the image) and retires output row s - 6
+    for (int s0 = 0; s0 < nsteps7; s0 += 7) {
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int s = s0 + u;
+        const bool load = s >= 3 && s < H + 3;
+        if (load) {
+          uint32_t a0[4], a1[4];               // channel c0 / c0 + 1
+          // fragment order: (row g, k lo), (row g+8, k lo), (row g, k hi), (row g+8, k hi)
+          a0[0] = __byte_perm(wn[0], wn[1], 0x5410); a1[0] = __byte_perm(wn[0], wn[1], 0x7632);
+          a0[1] = __byte_perm(wn[4], wn[5], 0x5410); a1[1] = __byte_perm(wn[4], wn[5], 0x7632);
+          a0[2] = __byte_perm(wn[2], wn[3], 0x5410); a1[2] = __byte_perm(wn[2], wn[3], 0x7632);
+          a0[3] = __byte_perm(wn[6], wn[7], 0x5410); a1[3] = __byte_perm(wn[6], wn[7], 0x7632);
+          prefetch(n + 1);
+          {
+            mma16816_init<T>(acc[u][0], a0, bfrag[0][0][0], bfrag[0][0][1], bv.x);      // output row s, slot s mod 7
+            mma16816_init<T>(acc[u][1], a1, bfrag[1][0][0], bfrag[1][0][1], bv.y);
+#pragma unroll
+            for (int dy = 1; dy < 7; ++dy) {
+              const int sl = (u - dy + 7) % 7;   // output row s - dy lives in slot (s - dy) mod 7
+              mma16816<T>(acc[sl][0], a0, bfrag[0][dy][0], bfrag[0][dy][1]);
+              mma16816<T>(acc[sl][1], a1, bfrag[1][dy][0], bfrag[1][dy][1]);
+            }
+          }
+          ++n;
+        }
+        const int done = (u + 1) % 7;          // slot of output row s - 6
+        const bool emit = s >= 6 && s < H + 6;
+        if (emit) {
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s), "r"(pack2<T>(acc[done][0][0], acc[done][1][0])) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][1], acc[done][1][1])) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * 8 * MM_XOUT * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][2], acc[done][1][2])) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * (8 * MM_XOUT + 1) * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][3], acc[done][1][3])) : "memory");
+        }
+        __syncthreads();
+        // every warp has turned this step's input row into fragments: refill its ring slot (step n - 1 + 8)
+        if (threadIdx.x == 0 && load) issue_next();
+        if (emit) {
+          uint4 q;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.x) : "r"(rb_s));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.y) : "r"(rb_s + 4));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.z) : "r"(rb_s + 8));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.w) : "r"(rb_s + 12));
+          if (rb_ok) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + rb_off) = q;
+          rb_off += row_bytes;
+          st_s = st_s + stg_flip; rb_s = rb_s + stg_flip; stg_flip = 0u - stg_flip;   // other staging buffer
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+bool dwconv7_mma_supported(int dtype, int C) {
+  return (dtype == GCV_BF16 || dtype == GCV_F16) && C % MM_CCH == 0 && C >= MM_CCH;
+}
+
+// y = conv_dw(x) + bias (no LayerNorm), x / y: [B,H,W,C] of `dtype`, taps: [49,C] fp32.
+int dwconv7_mma(int dtype, const void* x, void* y, const float* taps, const float* bias, int B, int H, int W, int C,
+                cudaStream_t stream) {
+  GCV_REQUIRE(dwconv7_mma_supported(dtype, C), "dwconv7_mma: needs a 16-bit dtype and C %% 32 == 0 (C=%d)", C);
+  GCV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+              "dwconv7_mma: x, y must be 16-byte aligned");
+  const int xtiles = (W + MM_XOUT - 1) / MM_XOUT, igroups = (B + MM_IMGS - 1) / MM_IMGS;
+  const int n_chunks = C / MM_CCH;
+  const int64_t n_tiles64 = (int64_t)xtiles * igroups;
+  GCV_REQUIRE(n_tiles64 * H < 2147483647LL, "dwconv7_mma: too many pipeline steps");
+  GCV_REQUIRE(((int64_t)igroups * MM_IMGS + 1) * H * W * C * 2 < 4294967295LL, "dwconv7_mma: tensor larger than 4 GiB");
+  const int n_tiles = (int)n_tiles64;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GCV_REQUIRE(n_chunks <= sms, "dwconv7_mma: C=%d has more channel chunks than the device has SMs", C);
+  const int tile_slots = sms / n_chunks;                    // tiles in flight; every one gets all its channel chunks
+  const int grid = (n_tiles < tile_slots ? n_tiles : tile_slots) * n_chunks;
+  const size_t smem = (size_t)MM_DEPTH * MM_SLOT_BYTES + 2 * MM_STAGE_BYTES + 8 * MM_DEPTH + 32 + 1024;
+  CUtensorMap tm;
+  {
+    EncodeTiledFn enc = mma_get_encode();
+    if (!enc) {
+      set_error("cuTensorMapEncodeTiled not resolvable (no CUDA driver?)");
+      return GCV_ERR_NO_DRIVER;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {MM_CCH, MM_XIN, 1, MM_IMGS};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType tdt = dtype == GCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = enc(&tm, tdt, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dwconv7_mma: cuTensorMapEncodeTiled failed: CUresult %d (B=%d H=%d W=%d C=%d)", (int)r, B, H, W, C);
+      return GCV_ERR_CUDA;
+    }
+  }
+  auto launch = [&](auto tag) -> int {
+    using T = decltype(tag);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(dwconv7_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr_done = true;
+    }
+    dwconv7_mma_kernel<T><<<grid, MM_THREADS, smem, stream>>>(tm, reinterpret_cast<T*>(y), taps, bias, B, H, W, C, xtiles,
+                                                             n_tiles, n_chunks);
+    return check_launch("dwconv7_mma");
+  };
+  return dtype == GCV_BF16 ? launch(__nv_bfloat16{}) : launch(__half{});
+}
+
+}  // namespace gcv

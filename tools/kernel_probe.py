@@ -40,7 +40,9 @@ if args.which in ("dwconv", "all"):
         taps, bias = torch.randn(49, C, device=dev) / 7, torch.randn(C, device=dev)
         lw, lb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
         timed(f"dwconv7_ln B{B} H{H} C{C}", lambda: L.dwconv7_ln(x, y, taps, bias, lw, lb, 1e-6, B, H, H, C),
-              2.0 * x.numel() * 2, "GB/s")
+              2.0 * x.numel() * 2 / 1e3, "TB/s")
+        timed(f"  layernorm_rows only B{B} H{H} C{C}", lambda: L.layernorm_rows(y, y, lw, lb, 1e-6, B * H * H, C),
+              2.0 * x.numel() * 2 / 1e3, "TB/s")
 if args.which in ("fc1", "all"):
     for (T, C) in ((3136, 96), (784, 192), (196, 384), (49, 768)):
         M = B * T
