@@ -50,8 +50,12 @@ int convt2x2_small(int dtype, const void* x, void* y, const float* w, const floa
                    int CI, int CO, cudaStream_t stream);
 bool mlp_fused_supported(int dtype, int C);
 int mlp_fused_trace(long long* out64);
-int mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
-              const float* gamma, void* x, int64_t M, int C, cudaStream_t stream);
+int mlp_fused(int dtype, const void* y, const float* ln_stats, float ln_eps, const void* w1, const float* b1,
+              const float* colsum1, const void* w2, const float* b2, const float* gamma, void* x, int64_t M, int C,
+              cudaStream_t stream);
+bool dwconv7_mma_supported(int dtype, int C);
+int dwconv7_mma(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias, int B, int H,
+                int W, int C, cudaStream_t stream);
 
 }  // namespace gcv
 
@@ -101,12 +105,33 @@ int gcv_debug_fused_trace(long long* out64) { return mlp_fused_trace(out64); }
 int gcv_mlp_fused_supported(int dtype, int C) { return mlp_fused_supported(dtype, C) ? 1 : 0; }
 int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, void* x, int64_t M, int C, void* stream) {
-  return mlp_fused(dtype, y, w1, b1, w2, b2, gamma, x, M, C, S(stream));
+  return mlp_fused(dtype, y, nullptr, 0.0f, w1, b1, nullptr, w2, b2, gamma, x, M, C, S(stream));
+}
+int gcv_mlp_fused_ln(int dtype, const void* y, const float* ln_stats, float ln_eps, const void* w1, const float* b1,
+                     const float* colsum1, const void* w2, const float* b2, const float* gamma, void* x, int64_t M,
+                     int C, void* stream) {
+  if (!ln_stats) {
+    set_error("gcv_mlp_fused_ln: ln_stats is NULL");
+    return GCV_ERR_BAD_ARG;
+  }
+  return mlp_fused(dtype, y, ln_stats, ln_eps, w1, b1, colsum1, w2, b2, gamma, x, M, C, S(stream));
 }
 
 int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias, const float* ln_w,
                    const float* ln_b, float eps, int B, int H, int W, int C, void* stream) {
   return dwconv7_ln(dtype, x, y, taps, bias, ln_w, ln_b, eps, B, H, W, C, S(stream));
+}
+int gcv_dwconv7_stats(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias, int B,
+                      int H, int W, int C, void* stream) {
+  if (!dwconv7_mma_supported(dtype, C)) {
+    set_error("gcv_dwconv7_stats: bf16/fp16 and C %% 32 == 0 only (dtype=%d C=%d)", dtype, C);
+    return GCV_ERR_UNSUPPORTED;
+  }
+  if (B <= 0 || H <= 0 || W <= 0) {
+    set_error("gcv_dwconv7_stats: bad shape B=%d H=%d W=%d", B, H, W);
+    return GCV_ERR_BAD_ARG;
+  }
+  return dwconv7_mma(dtype, x, y, stats, taps, bias, B, H, W, C, S(stream));
 }
 int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps, int B, int H,
                      int W, int C, void* stream) {

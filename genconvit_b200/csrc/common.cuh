@@ -111,6 +111,46 @@ __device__ __forceinline__ __half2 gelu_fast_h2(__half2 x) {
   return __hfma2(h, t, h);
 }
 
+// Row statistics of the folded LayerNorm (gcv_epilogue.ln_stats): (rstd, -mean * rstd) of row m from its per-chunk
+// partial sums, so that LN-folded pre-activation = acc * rs + rm * colsum[n] + bias[n].
+__device__ __forceinline__ float2 ln_row_scale(const float* stats, int64_t m, int chunks, int K, float eps) {
+  const float2* p = reinterpret_cast<const float2*>(stats) + m * chunks;
+  float s = 0.0f, q = 0.0f;
+  for (int i = 0; i < chunks; ++i) {
+    const float2 v = __ldg(p + i);
+    s += v.x; q += v.y;
+  }
+  const float inv = 1.0f / (float)K;
+  const float mean = s * inv;
+  const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, q * inv), 0.0f) + eps);
+  return make_float2(rstd, -mean * rstd);
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 gelu_pack8_h2(const __half2 x0, const __half2 x1, const __half2 x2, const __half2 x3) {
+  const __half2 g0 = gelu_fast_h2(x0), g1 = gelu_fast_h2(x1), g2 = gelu_fast_h2(x2), g3 = gelu_fast_h2(x3);
+  uint4 q;
+  if constexpr (sizeof(T) == 2 && !std::is_same<T, __half>::value) {
+    const float2 f0 = __half22float2(g0), f1 = __half22float2(g1), f2 = __half22float2(g2), f3 = __half22float2(g3);
+    q.x = pack2<T>(f0.x, f0.y); q.y = pack2<T>(f1.x, f1.y); q.z = pack2<T>(f2.x, f2.y); q.w = pack2<T>(f3.x, f3.y);
+  } else {
+    q.x = *reinterpret_cast<const uint32_t*>(&g0); q.y = *reinterpret_cast<const uint32_t*>(&g1);
+    q.z = *reinterpret_cast<const uint32_t*>(&g2); q.w = *reinterpret_cast<const uint32_t*>(&g3);
+  }
+  return q;
+}
+
+// folded LayerNorm + bias + GELU on 8 fp32 accumulators: x = w * rs + (rm * colsum + bias)
+template <typename T>
+__device__ __forceinline__ uint4 ln_bias_gelu_pack8(const float* w, const float rs, const float rm, const float4 s0,
+                                                    const float4 s1, const float4 b0, const float4 b1) {
+  return gelu_pack8_h2<T>(
+      __floats2half2_rn(fmaf(w[0], rs, fmaf(rm, s0.x, b0.x)), fmaf(w[1], rs, fmaf(rm, s0.y, b0.y))),
+      __floats2half2_rn(fmaf(w[2], rs, fmaf(rm, s0.z, b0.z)), fmaf(w[3], rs, fmaf(rm, s0.w, b0.w))),
+      __floats2half2_rn(fmaf(w[4], rs, fmaf(rm, s1.x, b1.x)), fmaf(w[5], rs, fmaf(rm, s1.y, b1.y))),
+      __floats2half2_rn(fmaf(w[6], rs, fmaf(rm, s1.z, b1.z)), fmaf(w[7], rs, fmaf(rm, s1.w, b1.w))));
+}
+
 // bias + GELU on 8 fp32 accumulators -> 8 packed 16-bit outputs (T = __half or __nv_bfloat16)
 template <typename T>
 __device__ __forceinline__ uint4 bias_gelu_pack8(const float* w, const float4 b0, const float4 b1) {
@@ -150,7 +190,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ---- GEMM epilogue (shared by the tcgen05 and the SIMT back ends) -----------------
 // One output element; see gcv_epilogue in the public header for the order of operations.
 template <typename T>
-__device__ __forceinline__ void epilogue_one(const gcv_epilogue& ep, int64_t m, int n, int N, float acc, void* D) {
+__device__ __forceinline__ void epilogue_one(const gcv_epilogue& ep, int64_t m, int n, int N, float acc, void* D,
+                                             int K = 0) {
+  if (ep.ln_stats) {
+    const float2 rs = ln_row_scale(ep.ln_stats, m, ep.ln_chunks, K, ep.ln_eps);
+    acc = fmaf(acc, rs.x, rs.y * __ldg(ep.ln_colsum + n));
+  }
   float v = acc + (ep.bias ? __ldg(ep.bias + n) : 0.0f);
   v = apply_act(v, ep.act);
   if (ep.eps) {

@@ -625,8 +625,8 @@ int dispatch(int dtype, F&& f) {
 }  // namespace
 
 bool dwconv7_mma_supported(int dtype, int C);
-int dwconv7_mma(int dtype, const void* x, void* y, const float* taps, const float* bias, int B, int H, int W, int C,
-                cudaStream_t stream);
+int dwconv7_mma(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias, int B, int H,
+                int W, int C, cudaStream_t stream);
 int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
                    cudaStream_t stream);
 
@@ -645,7 +645,7 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
   GCV_REQUIRE(C % 32 == 0 && C >= 32 && B > 0 && H > 0 && W > 0, "dwconv7_ln: C must be a multiple of 32 (C=%d)", C);
   if (dw_use_mma() && dwconv7_mma_supported(dtype, C) && C % 8 == 0 && C <= 2048) {
     // 16-bit modes: tensor-core depthwise conv (dwconv_mma.cu) into y, then the row LayerNorm in place
-    const int rc = dwconv7_mma(dtype, x, y, taps, bias, B, H, W, C, stream);
+    const int rc = dwconv7_mma(dtype, x, y, nullptr, taps, bias, B, H, W, C, stream);
     if (rc != GCV_OK) return rc;
     return layernorm_rows(dtype, y, y, ln_w, ln_b, eps, (int64_t)B * H * W, C, stream);
   }

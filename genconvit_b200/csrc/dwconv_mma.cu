@@ -98,7 +98,8 @@ __device__ __forceinline__ void mma16816_init(float (&d)[4], const uint32_t (&a)
 
 template <typename T>
 __global__ void __launch_bounds__(MM_THREADS, 1)
-dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, const float* __restrict__ taps,
+dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, float2* __restrict__ stats,
+                   const float* __restrict__ taps,
                    const float* __restrict__ bias, int B, int H, int W, int C, int xtiles, int n_tiles,
                    int n_chunks) {
   extern __shared__ uint8_t msm_dyn[];
@@ -198,15 +199,41 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, 
   };
   prefetch(0);
 
-  uint32_t stg_flip = MM_STAGE_BYTES;
+  uint32_t st_flip = MM_STAGE_BYTES, rb_flip = MM_STAGE_BYTES;
   const uint32_t row_bytes = (uint32_t)W * (uint32_t)C * 2u;
+  bool pending = false, rb_ok = false;
+  uint32_t rb_off = 0;
+  // staging tile -> global memory for the most recently parked output row (+ its LayerNorm partial sums)
+  auto readback = [&]() {
+    uint4 q;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.x) : "r"(rb_s));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.y) : "r"(rb_s + 4));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.z) : "r"(rb_s + 8));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.w) : "r"(rb_s + 12));
+    if (rb_ok) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + rb_off) = q;
+    if (stats) {
+      // LayerNorm partials of this chunk: sum and sum of squares over its 32 channels, taken from the rounded
+      // values the consumer will read; the 4 lanes of a pixel hold 8 channels each
+      const float2 f0 = unpack2<T>(q.x), f1 = unpack2<T>(q.y), f2 = unpack2<T>(q.z), f3 = unpack2<T>(q.w);
+      float sm = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      float sq = fmaf(f0.x, f0.x, f0.y * f0.y) + fmaf(f1.x, f1.x, f1.y * f1.y) +
+                 (fmaf(f2.x, f2.x, f2.y * f2.y) + fmaf(f3.x, f3.x, f3.y * f3.y));
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      // for the lane with rb_q == 0, rb_off = 64 * (pixel * n_chunks + cc)
+      if (rb_ok && rb_q == 0)
+        *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats) + (rb_off >> 3)) = make_float2(sm, sq);
+    }
+    rb_off += row_bytes;
+    rb_s += rb_flip; rb_flip = 0u - rb_flip;
+  };
   const int nsteps7 = ((H + 6 + 6) / 7) * 7;   // H + 6 steps, rounded up to whole turns of the 7-slot accumulator ring
   for (int i = 0; i < my_subs; ++i) {
     const int tile = tile0 + i * tile_step;
     const int ig = tile / xtiles, xt = tile - ig * xtiles;
     const int rb_b = ig * MM_IMGS + (rb_px >> 3), rb_x = xt * MM_XOUT + (rb_px & 7);
-    const bool rb_ok = rb_b < B && rb_x < W;
-    uint32_t rb_off = ((uint32_t)(rb_b * H) * (uint32_t)W + (uint32_t)rb_x) * (uint32_t)(C * 2) + (uint32_t)(cc * MM_CCH + 8 * rb_q) * 2u;   // output row 0
+    rb_ok = rb_b < B && rb_x < W;
+    rb_off = ((uint32_t)(rb_b * H) * (uint32_t)W + (uint32_t)rb_x) * (uint32_t)(C * 2) + (uint32_t)(cc * MM_CCH + 8 * rb_q) * 2u;   // output row 0
 
     float acc[7][2][4];                        // [output-row slot][channel][fragment]
     // rows 0..2 never see a dy = 0 tap (their first input row is row 0), so they start from the bias here; every
@@ -216,7 +243,9 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, 
       acc[sl][0][0] = acc[sl][0][1] = acc[sl][0][2] = acc[sl][0][3] = bv.x;
       acc[sl][1][0] = acc[sl][1][1] = acc[sl][1][2] = acc[sl][1][3] = bv.y;
     }
-    // step s consumes input row s - 3 (when inside the image) and retires output row s - 6
+    // step s consumes input row s - 3 (when inside the image) and retires output row s - 6.  Order inside a step:
+    // issue this step's MMAs, then (while they execute) move the row retired in the PREVIOUS step from the staging tile
+    // to global memory, then park the row retired now in the other staging tile, barrier.
     for (int s0 = 0; s0 < nsteps7; s0 += 7) {
 #pragma unroll
       for (int u = 0; u < 7; ++u) {
@@ -230,18 +259,18 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, 
           a0[2] = __byte_perm(wn[2], wn[3], 0x5410); a1[2] = __byte_perm(wn[2], wn[3], 0x7632);
           a0[3] = __byte_perm(wn[6], wn[7], 0x5410); a1[3] = __byte_perm(wn[6], wn[7], 0x7632);
           prefetch(n + 1);
-          {
-            mma16816_init<T>(acc[u][0], a0, bfrag[0][0][0], bfrag[0][0][1], bv.x);      // output row s, slot s mod 7
-            mma16816_init<T>(acc[u][1], a1, bfrag[1][0][0], bfrag[1][0][1], bv.y);
+          // dy = 6 first: it completes the row that is parked below, so that store waits for one MMA, not fourteen
 #pragma unroll
-            for (int dy = 1; dy < 7; ++dy) {
-              const int sl = (u - dy + 7) % 7;   // output row s - dy lives in slot (s - dy) mod 7
-              mma16816<T>(acc[sl][0], a0, bfrag[0][dy][0], bfrag[0][dy][1]);
-              mma16816<T>(acc[sl][1], a1, bfrag[1][dy][0], bfrag[1][dy][1]);
-            }
+          for (int dy = 6; dy >= 1; --dy) {
+            const int sl = (u - dy + 7) % 7;   // output row s - dy lives in slot (s - dy) mod 7
+            mma16816<T>(acc[sl][0], a0, bfrag[0][dy][0], bfrag[0][dy][1]);
+            mma16816<T>(acc[sl][1], a1, bfrag[1][dy][0], bfrag[1][dy][1]);
           }
+          mma16816_init<T>(acc[u][0], a0, bfrag[0][0][0], bfrag[0][0][1], bv.x);      // output row s, slot s mod 7
+          mma16816_init<T>(acc[u][1], a1, bfrag[1][0][0], bfrag[1][0][1], bv.y);
           ++n;
         }
+        if (pending) { readback(); pending = false; }
         const int done = (u + 1) % 7;          // slot of output row s - 6
         const bool emit = s >= 6 && s < H + 6;
         if (emit) {
@@ -249,22 +278,15 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tm_x, T* __restrict__ y, 
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][1], acc[done][1][1])) : "memory");
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * 8 * MM_XOUT * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][2], acc[done][1][2])) : "memory");
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_s + 4 * (8 * MM_XOUT + 1) * MM_STAGE_STRIDE), "r"(pack2<T>(acc[done][0][3], acc[done][1][3])) : "memory");
+          st_s += st_flip; st_flip = 0u - st_flip;                 // other staging buffer next time
+          pending = true;
         }
         __syncthreads();
         // every warp has turned this step's input row into fragments: refill its ring slot (step n - 1 + 8)
         if (threadIdx.x == 0 && load) issue_next();
-        if (emit) {
-          uint4 q;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.x) : "r"(rb_s));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.y) : "r"(rb_s + 4));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.z) : "r"(rb_s + 8));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q.w) : "r"(rb_s + 12));
-          if (rb_ok) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + rb_off) = q;
-          rb_off += row_bytes;
-          st_s = st_s + stg_flip; rb_s = rb_s + stg_flip; stg_flip = 0u - stg_flip;   // other staging buffer
-        }
       }
     }
+    if (pending) { readback(); pending = false; }    // the tile's last row (rb_off / rb_ok change with the tile)
   }
 }
 
@@ -275,8 +297,9 @@ bool dwconv7_mma_supported(int dtype, int C) {
 }
 
 // y = conv_dw(x) + bias (no LayerNorm), x / y: [B,H,W,C] of `dtype`, taps: [49,C] fp32.
-int dwconv7_mma(int dtype, const void* x, void* y, const float* taps, const float* bias, int B, int H, int W, int C,
-                cudaStream_t stream) {
+// stats (optional): [B*H*W][C/32] float2 = (sum, sum of squares) of y over each 32-channel chunk.
+int dwconv7_mma(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias, int B, int H,
+                int W, int C, cudaStream_t stream) {
   GCV_REQUIRE(dwconv7_mma_supported(dtype, C), "dwconv7_mma: needs a 16-bit dtype and C %% 32 == 0 (C=%d)", C);
   GCV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
               "dwconv7_mma: x, y must be 16-byte aligned");
@@ -322,7 +345,7 @@ int dwconv7_mma(int dtype, const void* x, void* y, const float* taps, const floa
       cudaFuncSetAttribute(dwconv7_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       attr_done = true;
     }
-    dwconv7_mma_kernel<T><<<grid, MM_THREADS, smem, stream>>>(tm, reinterpret_cast<T*>(y), taps, bias, B, H, W, C, xtiles,
+    dwconv7_mma_kernel<T><<<grid, MM_THREADS, smem, stream>>>(tm, reinterpret_cast<T*>(y), reinterpret_cast<float2*>(stats), taps, bias, B, H, W, C, xtiles,
                                                              n_tiles, n_chunks);
     return check_launch("dwconv7_mma");
   };

@@ -56,7 +56,7 @@ gemm_simt_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < N) epilogue_one<T>(ep, m, n, N, acc[i][j], D);
+      if (n < N) epilogue_one<T>(ep, m, n, N, acc[i][j], D, (int)K);
     }
   }
 }

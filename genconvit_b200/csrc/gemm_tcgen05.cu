@@ -76,7 +76,8 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
 }
 
 // MODE: 0 = staged epilogue, general (bias / act / layer-scale / residual); 1 = staged, bias + GELU only (packed fp16
-// math); 2 = element-wise cold path (ragged / fp32 / reparameterisation outputs).  Separate instantiations keep each
+// math); 2 = element-wise cold path (ragged / fp32 / reparameterisation outputs); 3 = mode 1 with the LayerNorm of
+// the A rows folded in (gcv_epilogue.ln_stats: per-row rstd / mean from partial sums, column sums in vec_gamma).  Separate instantiations keep each
 // epilogue within the 96 registers a 576-thread CTA leaves per thread.
 // DUO: the CTA pair of a 2-CTA cluster computes one 256 x block_n tile with cta_group::2 MMAs: each CTA stages its
 // own 128 rows of A and HALF of the B tile (so a stage is 16 KB + block_n/2 x 128 B instead of 16 KB + block_n x 128 B:
@@ -133,7 +134,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // bias / layer-scale vectors are read by every epilogue thread for every tile: keep them on chip
     for (int i = threadIdx.x; i < p.N; i += kThreads) {
       vec_bias[i] = p.ep.bias ? __ldg(p.ep.bias + i) : 0.0f;
-      vec_gamma[i] = p.ep.gamma ? __ldg(p.ep.gamma + i) : 1.0f;
+      vec_gamma[i] = MODE == 3 ? __ldg(p.ep.ln_colsum + i) : (p.ep.gamma ? __ldg(p.ep.gamma + i) : 1.0f);
     }
   }
   tc_fence_before();
@@ -217,7 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int sub = ew >> 2;                             // the 4 warps of a quarter take chunks sub, sub+4, ...
     const int chunks = p.block_n / 32;
     constexpr bool vec_ok = MODE != 2;
-    constexpr bool gelu_only = MODE == 1;
+    constexpr bool gelu_only = MODE == 1 || MODE == 3;
     uint8_t* my_stage = stage_base + ew * kStageWarp;
     const gcv_epilogue& ep = p.ep;
     // hand an accumulator stage back to the MMA warp (DUO: the leader CTA's, from either CTA)
@@ -232,10 +233,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_blk = DUO ? 2 * mw + (int)crank : mw;
       if (++as == p.acc_stages) as = 0;
       if (as == 0) aphase ^= 1;
-      mbar_wait(smem_u32(tmem_full + as), aphase);
-      tc_fence_after();
       const int64_t m_warp = (int64_t)m_blk * BM + quarter * 32;
       const int64_t m = m_warp + lane;
+      float2 lnrs = make_float2(1.0f, 0.0f);             // folded LayerNorm: (rstd, -mean * rstd) of this thread's row,
+      if constexpr (MODE == 3) {                         // fetched before blocking on the accumulator
+        if (m < p.M && sub < chunks) lnrs = ln_row_scale(ep.ln_stats, m, ep.ln_chunks, p.K, ep.ln_eps);
+      }
+      mbar_wait(smem_u32(tmem_full + as), aphase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.block_n);
       if (sub >= chunks) {                               // narrow tile: this warp has no chunk, release immediately
         tc_fence_before();
@@ -285,8 +290,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint4 q;
             if (gelu_only && n + 8 <= p.N) {
               // fc1 fast path: bias + GELU in packed fp16 arithmetic
-              q = bias_gelu_pack8<T>(w, *reinterpret_cast<const float4*>(vec_bias + n),
-                                     *reinterpret_cast<const float4*>(vec_bias + n + 4));
+              if constexpr (MODE == 3)
+                q = ln_bias_gelu_pack8<T>(w, lnrs.x, lnrs.y, *reinterpret_cast<const float4*>(vec_gamma + n),
+                                          *reinterpret_cast<const float4*>(vec_gamma + n + 4),
+                                          *reinterpret_cast<const float4*>(vec_bias + n),
+                                          *reinterpret_cast<const float4*>(vec_bias + n + 4));
+              else
+                q = bias_gelu_pack8<T>(w, *reinterpret_cast<const float4*>(vec_bias + n),
+                                       *reinterpret_cast<const float4*>(vec_bias + n + 4));
             } else {
               if (n + 8 <= p.N) {
                 if (p.vec_smem) {
@@ -496,10 +507,16 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);
   if (duo) grid &= ~1;
-  const int mode = !p.vec_ok ? 2
-                   : (p.vec_smem && ep->act == GCV_ACT_GELU && ep->bias && !ep->gamma && !ep->residual) ? 1 : 0;
+  int mode = !p.vec_ok ? 2
+             : (p.vec_smem && ep->act == GCV_ACT_GELU && ep->bias && !ep->gamma && !ep->residual) ? 1 : 0;
+  if (ep->ln_stats) {
+    GCV_REQUIRE(mode == 1 && ep->ln_colsum && ep->ln_chunks > 0 && N % 8 == 0,
+                "tcgen05 GEMM: the folded LayerNorm needs bias + GELU, a 16-bit row-major output and N %% 8 == 0, N <= %d",
+                kVecMaxN);
+    mode = 3;
+  }
   cudaError_t le = cudaSuccess;
-  static bool attr_set[2][3][2] = {};
+  static bool attr_set[2][4][2] = {};
   bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode][duo ? 1 : 0];
   auto launch = [&](auto kernel) {
     if (!attr_done) {
@@ -530,20 +547,24 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
     if (duo) {
       if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, true>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, true>);
+      else if (mode == 3) launch(gemm_tcgen05_kernel<__nv_bfloat16, 3, true>);
       else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, true>);
     } else {
       if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, false>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, false>);
+      else if (mode == 3) launch(gemm_tcgen05_kernel<__nv_bfloat16, 3, false>);
       else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, false>);
     }
   } else {
     if (duo) {
       if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, true>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, true>);
+      else if (mode == 3) launch(gemm_tcgen05_kernel<__half, 3, true>);
       else launch(gemm_tcgen05_kernel<__half, 2, true>);
     } else {
       if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, false>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, false>);
+      else if (mode == 3) launch(gemm_tcgen05_kernel<__half, 3, false>);
       else launch(gemm_tcgen05_kernel<__half, 2, false>);
     }
   }

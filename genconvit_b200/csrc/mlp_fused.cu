@@ -53,7 +53,7 @@ struct Cfg {
   static constexpr int OBUF = (2 * FCH + 2 * C <= 512) ? 2 : 1;
   static constexpr int RING = C <= 96 ? 4 : 3;
   static constexpr int STAGE_BYTES = kFEpiWarps * 32 * 64;   // per-warp 32 x 64 B output staging tiles
-  static constexpr int VEC_BYTES = ((HC + 2 * C) * 4 + 1023) / 1024 * 1024;
+  static constexpr int VEC_BYTES = ((2 * HC + 2 * C) * 4 + 1023) / 1024 * 1024;   // b1, colsum1 (LN fold), b2, gamma
   static constexpr int SMEM = kFCtrl + VEC_BYTES + XBUF * X_BYTES + 2 * H_BYTES + RING * SLOT + STAGE_BYTES + 1024;
   static_assert(C % 32 == 0 && C <= 192 && HC % FCH == 0 && NCH >= 2, "unsupported width");
   static_assert(XKB % KB1 == 0 && KB2 * C * 64 == SLOT && HKB % KB2 == 0, "slot geometry");
@@ -68,6 +68,9 @@ struct FParams {
   const float* b2;
   const float* gamma;
   void* x;                 // [M, C] residual in / result out (in place)
+  const float* ln_stats;   // folded LayerNorm (LN = true): [M][C/32] x (sum, sumsq) of the y rows; colsum1 [4C]
+  const float* colsum1;
+  float ln_eps;
 };
 
 #ifdef GCV_FUSED_TRACE
@@ -86,7 +89,7 @@ __device__ long long gcv_fused_trace[64];
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename T, int C>
+template <typename T, int C, bool LN>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const FParams p) {
@@ -108,7 +111,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   uint64_t* ring_empty = bars + 16 + K::RING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * K::RING);
   float* vec_b1 = reinterpret_cast<float*>(gbase + kFCtrl);           // [HC]
-  float* vec_b2 = vec_b1 + K::HC;                                      // [C]
+  float* vec_s1 = vec_b1 + K::HC;                                      // [HC] column sums of W1 (LN fold)
+  float* vec_b2 = vec_s1 + K::HC;                                      // [C]
   float* vec_g = vec_b2 + C;                                           // [C]
   const uint32_t x_smem = base + kFCtrl + K::VEC_BYTES;               // X0 (, X1)
   const uint32_t h_smem = x_smem + K::XBUF * K::X_BYTES;              // H0, H1
@@ -143,7 +147,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < K::HC; i += kFThreads) vec_b1[i] = __ldg(p.b1 + i);
+  for (int i = threadIdx.x; i < K::HC; i += kFThreads) {
+    vec_b1[i] = __ldg(p.b1 + i);
+    if constexpr (LN) vec_s1[i] = __ldg(p.colsum1 + i);
+  }
   for (int i = threadIdx.x; i < C; i += kFThreads) {
     vec_b2[i] = __ldg(p.b2 + i);
     vec_g[i] = __ldg(p.gamma + i);
@@ -393,10 +400,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       }
     };
     int pending = -1;
+    int ln_ti = -1;
+    float2 lnrs = make_float2(1.0f, 0.0f);   // folded LayerNorm: (rstd, -mean * rstd) of this thread's row of tile ln_ti
+    float2 ln_next = lnrs;                   // ... and of the following tile (prefetched)
 #pragma unroll 1
     for (int g = grp; g < total; g += 2) {
       const int ti = g / K::NCH, j = g - ti * K::NCH;
       const int b = grp;
+      if constexpr (LN) {
+        // row statistics of tile ti: fetched while the previous tile's last chunk is still in flight
+        if (ti != ln_ti) {
+          if (ln_ti >= 0) {
+            lnrs = ln_next;
+          } else {
+            const int64_t m = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + row;
+            lnrs = m < p.M ? ln_row_scale(p.ln_stats, m, C / 32, C, p.ln_eps) : make_float2(1.0f, 0.0f);
+          }
+          ln_ti = ti;
+          const int64_t mn = (int64_t)((int)blockIdx.x + (ti + 1) * (int)gridDim.x) * FM + row;
+          ln_next = mn < p.M ? ln_row_scale(p.ln_stats, mn, C / 32, C, p.ln_eps) : make_float2(1.0f, 0.0f);
+        }
+      }
       const uint32_t n_use = (uint32_t)(g >> 1);
       TR_BEGIN
       mbar_wait(smem_u32(s_full + b), n_use & 1);
@@ -421,9 +445,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         const float* bj = vec_b1 + j * FCH + kb * 32;
         uint4 pk[4];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq)
-          pk[gq] = bias_gelu_pack8<T>(v + gq * 8, *reinterpret_cast<const float4*>(bj + gq * 8),
-                                      *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+        for (int gq = 0; gq < 4; ++gq) {
+          if constexpr (LN) {
+            const float* sj = bj + K::HC;    // vec_s1 follows vec_b1
+            pk[gq] = ln_bias_gelu_pack8<T>(v + gq * 8, lnrs.x, lnrs.y, *reinterpret_cast<const float4*>(sj + gq * 8),
+                                           *reinterpret_cast<const float4*>(sj + gq * 8 + 4),
+                                           *reinterpret_cast<const float4*>(bj + gq * 8),
+                                           *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+          } else {
+            pk[gq] = bias_gelu_pack8<T>(v + gq * 8, *reinterpret_cast<const float4*>(bj + gq * 8),
+                                        *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+          }
+        }
         TR_BEGIN
         if (hk == 0) mbar_wait(smem_u32(h_empty + b), (n_use & 1) ^ 1);   // fc2 that last read this buffer retired
         TR_END(1)
@@ -490,8 +523,8 @@ int fused_map(CUtensorMap* map, int dtype, const void* ptr, int64_t rows, int64_
   return GCV_OK;
 }
 
-template <typename T, int C>
-int launch_fused(int dtype, const void* y, const void* w1, const void* w2, const FParams& p, cudaStream_t stream) {
+template <typename T, int C, bool LN>
+int launch_fused_impl(int dtype, const void* y, const void* w1, const void* w2, const FParams& p, cudaStream_t stream) {
   using K = Cfg<C>;
   CUtensorMap my, m1, m2;
   int rc = fused_map(&my, dtype, y, p.M, C, FM);
@@ -500,7 +533,7 @@ int launch_fused(int dtype, const void* y, const void* w1, const void* w2, const
   if ((rc = fused_map(&m2, dtype, w2, C, K::HC, C))) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<T, C, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(fused MLP smem=%d): %s", K::SMEM, cudaGetErrorString(e));
       return GCV_ERR_CUDA;
@@ -514,8 +547,14 @@ int launch_fused(int dtype, const void* y, const void* w1, const void* w2, const
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = p.tiles < sms ? p.tiles : sms;
-  mlp_fused_kernel<T, C><<<grid, kFThreads, K::SMEM, stream>>>(my, m1, m2, p);
+  mlp_fused_kernel<T, C, LN><<<grid, kFThreads, K::SMEM, stream>>>(my, m1, m2, p);
   return check_launch("mlp_fused");
+}
+
+template <typename T, int C>
+int launch_fused(int dtype, const void* y, const void* w1, const void* w2, const FParams& p, cudaStream_t stream) {
+  return p.ln_stats ? launch_fused_impl<T, C, true>(dtype, y, w1, w2, p, stream)
+                    : launch_fused_impl<T, C, false>(dtype, y, w1, w2, p, stream);
 }
 
 }  // namespace
@@ -531,10 +570,12 @@ int mlp_fused_trace(long long* out64) {
 
 bool mlp_fused_supported(int dtype, int C) { return (dtype == GCV_BF16 || dtype == GCV_F16) && (C == 96 || C == 192); }
 
-int mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
-              const float* gamma, void* x, int64_t M, int C, cudaStream_t stream) {
+int mlp_fused(int dtype, const void* y, const float* ln_stats, float ln_eps, const void* w1, const float* b1,
+              const float* colsum1, const void* w2, const float* b2, const float* gamma, void* x, int64_t M, int C,
+              cudaStream_t stream) {
   GCV_REQUIRE(mlp_fused_supported(dtype, C), "mlp_fused: bf16/fp16 and C in {96,192} only (dtype=%d C=%d)", dtype, C);
   GCV_REQUIRE(M > 0 && y && w1 && w2 && b1 && b2 && gamma && x, "mlp_fused: bad arguments");
+  GCV_REQUIRE(!ln_stats || colsum1, "mlp_fused: the folded LayerNorm needs the column sums of w1");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   GCV_REQUIRE(al16(y) && al16(w1) && al16(w2) && al16(x), "mlp_fused: pointers must be 16-byte aligned");
   FParams p{};
@@ -543,6 +584,7 @@ int mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const v
   p.idesc1 = umma_idesc_f16(dtype == GCV_BF16, FM, FCH);
   p.idesc2 = umma_idesc_f16(dtype == GCV_BF16, FM, C);
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.x = x;
+  p.ln_stats = ln_stats; p.colsum1 = colsum1; p.ln_eps = ln_eps;
   if (dtype == GCV_BF16) {
     return C == 96 ? launch_fused<__nv_bfloat16, 96>(dtype, y, w1, w2, p, stream)
                    : launch_fused<__nv_bfloat16, 192>(dtype, y, w1, w2, p, stream);

@@ -22,6 +22,10 @@ DEPTHS = (3, 3, 9, 3)
 DIMS = (96, 192, 384, 768)
 # the fused fc1->GELU->fc2 kernel (stages 0-1); GCV_NO_FUSED_MLP=1 falls back to two GEMM launches (A/B timing)
 FUSED_MLP = os.environ.get("GCV_NO_FUSED_MLP", "0") != "1"
+# 16-bit modes: depthwise conv on the tensor cores writing the un-normalised output + LayerNorm partial sums, with the
+# LayerNorm folded into fc1 (weights pre-scaled by the LN weight, row statistics applied in the fc1 epilogue), so the
+# block makes no separate normalisation pass.  GCV_NO_LNFOLD=1 keeps the explicit dwconv7_ln kernel (A/B timing).
+LN_FOLD = os.environ.get("GCV_NO_LNFOLD", "0") != "1"
 
 
 def _f32(t, dev):
@@ -57,7 +61,16 @@ class PackedConvNeXt:
             for k in range(depth):
                 q = f"{p}blocks.{k}."
                 c = DIMS[s]
-                st["blocks"].append(dict(
+                fold = {}
+                if dt != torch.float32:
+                    # LayerNorm folded into fc1: W1' = W1 diag(ln_w) (rounded to the kernel dtype), its column sums
+                    # taken from the ROUNDED matrix (so a constant row still cancels exactly), b1' = b1 + W1 ln_b
+                    w1 = sd[q + "mlp.fc1.weight"].detach().to(device=dev, dtype=torch.float32)
+                    lw, lb = _f32(sd[q + "norm.weight"], dev), _f32(sd[q + "norm.bias"], dev)
+                    w1f = (w1 * lw[None, :]).to(dt).contiguous()
+                    fold = dict(fc1_wf=w1f, fc1_cs=w1f.float().sum(dim=1).contiguous(),
+                                fc1_bf=(_f32(sd[q + "mlp.fc1.bias"], dev) + w1 @ lb).contiguous())
+                st["blocks"].append(dict(fold, 
                     taps=_f32(sd[q + "conv_dw.weight"].reshape(c, 49).t(), dev),     # [49, C]
                     dw_b=_f32(sd[q + "conv_dw.bias"], dev),
                     ln_w=_f32(sd[q + "norm.weight"], dev), ln_b=_f32(sd[q + "norm.bias"], dev),
@@ -105,16 +118,28 @@ class PackedConvNeXt:
                 segs, m = new, m2
             y = _empty((m, c), dt, dev)
             fused = FUSED_MLP and backend == L.GEMM_AUTO and L.mlp_fused_supported(dt, c)
+            fold = LN_FOLD and backend == L.GEMM_AUTO and dt != torch.float32
+            stats = _empty((m, c // 32, 2), torch.float32, dev) if fold else None
             hid = None if fused else _empty((m, 4 * c), dt, dev)
             for blk in st["blocks"]:
                 r = 0
                 for b, h, w in segs:
-                    L.dwconv7_ln(x[r:], y[r:], blk["taps"], blk["dw_b"], blk["ln_w"], blk["ln_b"], 1e-6, b, h, w, c)
+                    if fold:
+                        L.dwconv7_stats(x[r:], y[r:], stats[r:], blk["taps"], blk["dw_b"], b, h, w, c)
+                    else:
+                        L.dwconv7_ln(x[r:], y[r:], blk["taps"], blk["dw_b"], blk["ln_w"], blk["ln_b"], 1e-6, b, h, w, c)
                     r += b * h * w
-                if fused:
+                if fused and fold:
+                    L.mlp_fused_ln(y, stats, 1e-6, blk["fc1_wf"], blk["fc1_bf"], blk["fc1_cs"], blk["fc2_w"],
+                                   blk["fc2_b"], blk["gamma"], x, m, c)
+                elif fused:
                     L.mlp_fused(y, blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], blk["gamma"], x, m, c)
                 else:
-                    L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
+                    if fold:
+                        L.gemm(y, blk["fc1_wf"], hid, m, 4 * c, c, bias=blk["fc1_bf"], act=L.ACT_GELU, ln_stats=stats,
+                               ln_colsum=blk["fc1_cs"], ln_eps=1e-6, backend=backend)
+                    else:
+                        L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
                     L.gemm(hid, blk["fc2_w"], x, m, c, 4 * c, bias=blk["fc2_b"], gamma=blk["gamma"], residual=x,
                            ldr=c, backend=backend)
         c = DIMS[3]

@@ -22,7 +22,7 @@ GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 EXPORTS = [
-    "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_dwconv7_ln", "gcv_ln_patchify2",
+    "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
     "gcv_im2col3x3", "gcv_maxpool2", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
 ]
@@ -35,6 +35,7 @@ class Epilogue(C.Structure):
         ("ldr", C.c_int64), ("eps", C.c_void_p), ("eps_c", C.c_int32), ("eps_hw", C.c_int32),
         ("mu_out", C.c_void_p), ("store", C.c_int32), ("ps_h", C.c_int32), ("ps_w", C.c_int32),
         ("ps_co", C.c_int32), ("ldd", C.c_int64), ("out_f32", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_chunks", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 
@@ -61,7 +62,9 @@ def load():
     lib.gcv_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, i64, i64, i64, C.POINTER(Epilogue), vp]
     lib.gcv_mlp_fused_supported.argtypes = [i32, i32]
     lib.gcv_mlp_fused.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.gcv_mlp_fused_ln.argtypes = [i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     lib.gcv_dwconv7_ln.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
+    lib.gcv_dwconv7_stats.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_ln_patchify2.argtypes = [i32, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp]
     lib.gcv_stem_patchify_nchw.argtypes = [i32, vp, vp, i32, i32, i32, vp]
     lib.gcv_stem_patchify_nhwc.argtypes = [i32, vp, vp, i32, i32, i32, vp]
@@ -78,7 +81,7 @@ def load():
         fn = getattr(lib, name)
         if name not in ("gcv_last_error",):
             fn.restype = C.c_int
-    if lib.gcv_abi_version() != 1:
+    if lib.gcv_abi_version() != 2:
         raise GcvError("libgenconvit_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -130,7 +133,7 @@ class _Timed:
 
 def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_NONE, gamma=None, residual=None,
          ldr=None, eps=None, eps_c=0, eps_hw=0, mu_out=None, store=STORE_ROWS, ps=(0, 0, 0), out_f32=False,
-         backend=GEMM_AUTO):
+         ln_stats=None, ln_colsum=None, ln_eps=0.0, backend=GEMM_AUTO):
     """D[M,N] = epilogue(A[M,K] @ B[N,K]^T); see gcv_gemm / gcv_epilogue."""
     global launches
     require_cuda(a, "gemm")
@@ -147,12 +150,16 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     ep.ps_h, ep.ps_w, ep.ps_co = ps
     ep.ldd = ldd if ldd is not None else N
     ep.out_f32 = 1 if out_f32 else 0
+    ep.ln_stats = ln_stats.data_ptr() if ln_stats is not None else None
+    ep.ln_colsum = ln_colsum.data_ptr() if ln_colsum is not None else None
+    ep.ln_chunks = (K // 32) if ln_stats is not None else 0
+    ep.ln_eps = ln_eps
     lda_, ldb_ = (lda if lda is not None else K), (ldb if ldb is not None else K)
     tc = backend == GEMM_TCGEN05 or backend >= 1000 or (
         backend == GEMM_AUTO and a.dtype != torch.float32 and K % 8 == 0 and lda_ % 8 == 0 and ldb_ % 8 == 0
         and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
     tag = f"M{M} N{N} K{K} act{act}" + ("+res" if residual is not None else "") + ("+eps" if eps is not None else "") + \
-        ("+ps" if store else "")
+        ("+ps" if store else "") + ("+ln" if ln_stats is not None else "")
     with _Timed("gemm_tcgen05" if tc else "gemm_simt", 2.0 * M * N * K, tag):
         rc = load().gcv_gemm(backend, DTYPE_CODE[a.dtype], _p(a), lda_, _p(b), ldb_, _p(d), M, N, K, C.byref(ep),
                              _stream())
@@ -169,6 +176,20 @@ def mlp_fused(y, w1, b1, w2, b2, gamma, x, M, c):
     _run("mlp_fused", 16.0 * M * c * c, lambda: load().gcv_mlp_fused(
         DTYPE_CODE[y.dtype], _p(y), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(x), M, c, _stream()),
         f"M{M} C{c}")
+
+
+def mlp_fused_ln(y, stats, ln_eps, w1, b1, colsum1, w2, b2, gamma, x, M, c):
+    """mlp_fused with the block's LayerNorm folded into fc1 (y = un-normalised dwconv output); see gcv_mlp_fused_ln."""
+    _run("mlp_fused", 16.0 * M * c * c, lambda: load().gcv_mlp_fused_ln(
+        DTYPE_CODE[y.dtype], _p(y), _p(stats), ln_eps, _p(w1), _p(b1), _p(colsum1), _p(w2), _p(b2), _p(gamma), _p(x),
+        M, c, _stream()), f"M{M} C{c} +ln")
+
+
+def dwconv7_stats(x, y, stats, taps, bias, B, H, W, Cc):
+    """y = dwconv7x7(x) + bias on the tensor cores, stats = LayerNorm partial sums; see gcv_dwconv7_stats."""
+    _run("dwconv7_mma", 2.0 * B * H * W * Cc * x.element_size(), lambda: load().gcv_dwconv7_stats(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(stats), _p(taps), _p(bias), B, H, W, Cc, _stream()),
+        f"B{B} H{H} W{W} C{Cc}")
 
 
 def dwconv7_ln(x, y, taps, bias, ln_w, ln_b, eps, B, H, W, Cc):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GCV_ABI_VERSION 1
+#define GCV_ABI_VERSION 2
 
 enum gcv_dtype { GCV_F32 = 0, GCV_BF16 = 1, GCV_F16 = 2 };
 enum gcv_act { GCV_ACT_NONE = 0, GCV_ACT_GELU = 1, GCV_ACT_RELU = 2, GCV_ACT_LEAKY = 3 };
@@ -45,7 +45,8 @@ enum gcv_status {
 
 /*
  * Epilogue applied to the fp32 accumulator of both GEMM back ends, in this
- * order:  v = acc + bias[n];  v = act(v);
+ * order:  if (ln_stats) acc = rstd[m] * (acc - mean[m] * ln_colsum[n]);   (folded LayerNorm, see below)
+ *         v = acc + bias[n];  v = act(v);
  *         if (eps)      { mu = v; v = eps[m, perm(n)] * exp(0.5*mu) + mu; }
  *         if (gamma)    v = gamma[n] * v;
  *         if (residual) v = residual[m, n] + v;
@@ -68,6 +69,15 @@ typedef struct gcv_epilogue {
   int32_t ps_h, ps_w, ps_co;
   int64_t ldd;
   int32_t out_f32;
+  /* Folded LayerNorm over the K (= channel) dimension of A (timm ConvNeXtBlock.norm feeding mlp.fc1): A holds the
+   * un-normalised rows, B holds W * diag(ln_weight), bias holds b + W * ln_bias, ln_colsum[n] = sum_k B[n,k], and
+   * ln_stats holds per-row partial sums [M][ln_chunks] of (sum, sum of squares) over chunks of K (written by
+   * gcv_dwconv7_stats); mean = sum/K, rstd = rsqrt(sumsq/K - mean^2 + ln_eps).  NULL = no fold.
+   * tcgen05 back end: only together with bias + GELU and a 16-bit row-major output. */
+  const float* ln_stats;
+  const float* ln_colsum;
+  int32_t ln_chunks;
+  float ln_eps;
 } gcv_epilogue;
 
 /* -- library ------------------------------------------------------------- */
@@ -96,6 +106,12 @@ int gcv_gemm(int backend, int dtype, const void* A, int64_t lda, const void* B, 
 int gcv_mlp_fused_supported(int dtype, int C);
 int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, void* x, int64_t M, int C, void* stream);
+/* Same with the block's LayerNorm folded in (see gcv_epilogue.ln_stats): y holds the un-normalised depthwise-conv
+ * output, w1 = W1 * diag(ln_weight), b1 = b1 + W1 * ln_bias, colsum1[n] = sum_k w1[n,k], ln_stats from
+ * gcv_dwconv7_stats ([M][C/32] x (sum, sumsq)). */
+int gcv_mlp_fused_ln(int dtype, const void* y, const float* ln_stats, float ln_eps, const void* w1, const float* b1,
+                     const float* colsum1, const void* w2, const float* b2, const float* gamma, void* x, int64_t M,
+                     int C, void* stream);
 
 /* -- ConvNeXt memory-bound kernels ----------------------------------------
  * gcv_dwconv7_ln: timm ConvNeXtBlock.conv_dw (7x7, pad 3, groups=C, bias) fused
@@ -111,6 +127,12 @@ int gcv_mlp_fused(int dtype, const void* y, const void* w1, const float* b1, con
 int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float* bias,
                    const float* ln_w, const float* ln_b, float eps,
                    int B, int H, int W, int C, void* stream);
+/* gcv_dwconv7_stats (bf16/fp16, C % 32 == 0): y = conv_dw(x) + bias WITHOUT the LayerNorm, on the tensor cores
+ *   (banded-Toeplitz m16n8k16 MMAs, see csrc/dwconv_mma.cu), plus the LayerNorm partial sums of y:
+ *   stats [B*H*W][C/32] x (sum, sum of squares) fp32 over each 32-channel chunk, for the folded LayerNorm of
+ *   gcv_gemm (gcv_epilogue.ln_stats) / gcv_mlp_fused_ln.  stats may be NULL. */
+int gcv_dwconv7_stats(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias,
+                      int B, int H, int W, int C, void* stream);
 int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps,
                      int B, int H, int W, int C, void* stream);
 int gcv_stem_patchify_nchw(int dtype, const float* x, void* a, int B, int H, int W, void* stream);

@@ -23,14 +23,15 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(dll, s), f"{s} declared in the header but not exported"
     assert sorted(lib.EXPORTS) == syms
     dll.gcv_abi_version.restype = ctypes.c_int
-    assert dll.gcv_abi_version() == 1
+    assert dll.gcv_abi_version() == 2
 
 
 def test_epilogue_struct_matches_header_layout():
     from genconvit_b200 import lib
     # 8-byte pointers / int64 with natural alignment, as the C compiler lays out gcv_epilogue
-    assert ctypes.sizeof(lib.Epilogue) == 96
-    assert lib.Epilogue.ldd.offset == 80 and lib.Epilogue.mu_out.offset == 56
+    assert ctypes.sizeof(lib.Epilogue) == 120
+    assert lib.Epilogue.ldd.offset == 80 and lib.Epilogue.mu_out.offset == 56 and lib.Epilogue.ln_stats.offset == 96
+    assert lib.Epilogue.ln_eps.offset == 116
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():

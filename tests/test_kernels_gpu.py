@@ -208,6 +208,80 @@ def test_dwconv7_ln(cfg, dtype):
     _close(out, want, TOL[dtype] * 2, f"dwconv {cfg}")
 
 
+def _fold_ln_into_fc1(w1, b1, lw, lb, dtype):
+    """W1' = W1 diag(lw) rounded to `dtype`, column sums of the rounded matrix, b1' = b1 + W1 lb (what engine.py packs)."""
+    w1f = (w1.float() * lw[None, :]).to(dtype).contiguous()
+    return w1f, w1f.float().sum(dim=1).contiguous(), (b1 + w1.float() @ lb).contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cfg", [(2, 56, 56, 96), (17, 28, 28, 192), (33, 14, 14, 384), (16, 7, 7, 768), (1, 3, 3, 768),
+                                 (1, 9, 13, 96), (3, 5, 20, 64), (40, 7, 7, 384), (2, 8, 8, 160)])
+def test_dwconv7_stats(cfg, dtype):
+    """Tensor-core depthwise conv: un-normalised output + LayerNorm partial sums (sum, sumsq per 32-channel chunk)."""
+    L = _lib()
+    B, H, W, C = cfg
+    x = _rand(B, H, W, C, dtype=dtype, seed=1)
+    w, bias = _rand(C, 1, 7, 7, seed=2, scale=1 / 7), _rand(C, seed=3, scale=0.1)
+    # the kernel rounds the taps to the activation type, like every other 16-bit weight
+    wq = w.to(dtype).float()
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), wq, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    out = torch.full_like(x, float("nan"))
+    stats = torch.full((B * H * W, C // 32, 2), float("nan"), device=DEV)
+    L.dwconv7_stats(x, out, stats, w.reshape(C, 49).t().contiguous(), bias, B, H, W, C)
+    torch.cuda.synchronize()
+    _close(out, want, TOL[dtype], f"dwconv7_stats {cfg}")
+    # the statistics describe the ROUNDED output exactly (up to fp32 summation order)
+    o = out.float().view(B * H * W, C // 32, 32)
+    _close(stats[..., 0], o.sum(-1), 1e-5, "chunk sums")
+    _close(stats[..., 1], (o * o).sum(-1), 1e-5, "chunk sums of squares")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(1000, 384, 96), (4096 + 13, 1536, 384), (300, 3072, 768), (128 * 148 * 2 + 5, 768, 192)])
+def test_gemm_folded_layernorm(shape, dtype):
+    """fc1(LayerNorm(v)) computed as GELU(rstd * (v W'^T - mean * colsum) + b') from per-chunk partial sums."""
+    L = _lib()
+    M, N, K = shape
+    v = (_rand(M, K, seed=1) * 1.7 + 0.4).to(dtype)
+    w1, b1 = _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3, scale=0.3)
+    lw, lb = _rand(K, seed=4).abs() + 0.5, _rand(K, seed=5, scale=0.2)
+    w1f, cs, b1f = _fold_ln_into_fc1(w1, b1, lw, lb, dtype)
+    vc = v.float().view(M, K // 32, 32)
+    stats = torch.stack([vc.sum(-1), (vc * vc).sum(-1)], dim=-1).contiguous()
+    want = F.gelu(F.layer_norm(v.float(), (K,), lw, lb, 1e-6) @ w1.float().t() + b1)
+    d = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+    L.gemm(v, w1f, d, M, N, K, bias=b1f, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6)
+    torch.cuda.synchronize()
+    _close(d, want, TOL[dtype], f"folded LN gemm {shape}")
+    # the SIMT back end implements the same epilogue
+    if M <= 1000:
+        d2 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+        L.gemm(v, w1f, d2, M, N, K, bias=b1f, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6, backend=L.GEMM_SIMT)
+        _close(d2, want, TOL[dtype], f"folded LN simt {shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C", [96, 192])
+@pytest.mark.parametrize("M", [1000, 148 * 128 + 77])
+def test_mlp_fused_folded_layernorm(M, C, dtype):
+    """x += gamma * (GELU(LN(v) W1^T + b1) W2^T + b2) with the LayerNorm folded into the fused kernel's fc1 epilogue."""
+    L = _lib()
+    v, x = (_rand(M, C, seed=1) * 1.3 - 0.2).to(dtype), _rand(M, C, dtype=dtype, seed=2)
+    w1, b1 = _rand(4 * C, C, seed=3, scale=C ** -0.5), _rand(4 * C, seed=5, scale=0.3)
+    w2 = _rand(C, 4 * C, dtype=dtype, seed=4, scale=(4 * C) ** -0.5)
+    b2, gamma = _rand(C, seed=6, scale=0.3), _rand(C, seed=7).abs()
+    lw, lb = _rand(C, seed=8).abs() + 0.5, _rand(C, seed=9, scale=0.2)
+    w1f, cs, b1f = _fold_ln_into_fc1(w1, b1, lw, lb, dtype)
+    vc = v.float().view(M, C // 32, 32)
+    stats = torch.stack([vc.sum(-1), (vc * vc).sum(-1)], dim=-1).contiguous()
+    hid = F.gelu(F.layer_norm(v.float(), (C,), lw, lb, 1e-6) @ w1.float().t() + b1).to(dtype).float()
+    want = x.float() + gamma * (hid @ w2.float().t() + b2)
+    L.mlp_fused_ln(v, stats, 1e-6, w1f, b1f, cs, w2, b2, gamma, x, M, C)
+    torch.cuda.synchronize()
+    _close(x, want, 2e-2 if dtype == torch.bfloat16 else 4e-3, f"mlp_fused_ln M={M} C={C}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("cfg", [(2, 56, 56, 96), (1, 7, 7, 384), (2, 14, 14, 192)])
 def test_ln_patchify2(cfg, dtype):
