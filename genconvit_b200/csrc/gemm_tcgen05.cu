@@ -45,6 +45,7 @@ struct Params {
   int64_t M;
   int N, K;
   int block_n, num_stages, acc_stages;
+  int n_sub, mma_n;    // a tile's accumulator is n_sub MMAs of width mma_n side by side (block_n = n_sub * mma_n)
   int tiles_m, tiles_n;
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
@@ -77,7 +78,9 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
 
 // MODE: 0 = staged epilogue, general (bias / act / layer-scale / residual); 1 = staged, bias + GELU only (packed fp16
 // math); 2 = element-wise cold path (ragged / fp32 / reparameterisation outputs); 3 = mode 1 with the LayerNorm of
-// the A rows folded in (gcv_epilogue.ln_stats: per-row rstd / mean from partial sums, column sums in vec_gamma).  Separate instantiations keep each
+// the A rows folded in (gcv_epilogue.ln_stats: per-row rstd / mean from partial sums, column sums in vec_gamma);
+// 4 = staged, bias + layer-scale + residual only (ConvNeXt fc2): the residual rows are fetched a chunk ahead (the
+// first chunk before the accumulator wait), so their HBM latency is off the epilogue's critical path.  Separate instantiations keep each
 // epilogue within the 96 registers a 576-thread CTA leaves per thread.
 // DUO: the CTA pair of a 2-CTA cluster computes one 256 x block_n tile with cta_group::2 MMAs: each CTA stages its
 // own 128 rows of A and HALF of the B tile (so a stage is 16 KB + block_n/2 x 128 B instead of 16 KB + block_n x 128 B:
@@ -100,8 +103,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t b_rows = DUO ? (uint32_t)p.block_n >> 1 : (uint32_t)p.block_n;     // B rows staged by this CTA
-  const uint32_t a_bytes = BM * BK * 2, b_bytes = b_rows * BK * 2;
+  const uint32_t b_rows = DUO ? (uint32_t)p.mma_n >> 1 : (uint32_t)p.mma_n;     // B rows this CTA stages per MMA
+  const uint32_t a_bytes = BM * BK * 2, sub_bytes = b_rows * BK * 2, b_bytes = (uint32_t)p.n_sub * sub_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -165,7 +168,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // both CTAs' loads complete on the leader's barrier, which therefore expects two stages' worth of bytes
             if (leader) mbar_expect_tx(fb, 2 * stage_bytes);
             tma_load_2d_2sm(sa, &tmap_a, fb, kb * BK, m_blk * BM);
-            tma_load_2d_2sm(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n + (int)(crank * b_rows));
+            for (int j = 0; j < p.n_sub; ++j)
+              tma_load_2d_2sm(sa + a_bytes + j * sub_bytes, &tmap_b, fb, kb * BK,
+                              n_blk * p.block_n + j * p.mma_n + (int)(crank * b_rows));
           } else {
             mbar_expect_tx(fb, stage_bytes);
             tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
@@ -194,9 +199,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int kmma = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
           for (int k = 0; k < kmma; ++k) {
             const uint64_t ad = umma_desc(sa + k * 32);
-            const uint64_t bd = umma_desc(sa + a_bytes + k * 32);
-            if constexpr (DUO) tc_mma_2sm(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
-            else tc_mma(d_tmem, ad, bd, p.idesc, (kb | k) ? 1u : 0u);
+            if constexpr (DUO) {
+              for (int j = 0; j < p.n_sub; ++j)
+                tc_mma_2sm(d_tmem + (uint32_t)(j * p.mma_n), ad, umma_desc(sa + a_bytes + j * sub_bytes + k * 32), p.idesc,
+                           (kb | k) ? 1u : 0u);
+            } else {
+              tc_mma(d_tmem, ad, umma_desc(sa + a_bytes + k * 32), p.idesc, (kb | k) ? 1u : 0u);
+            }
           }
           if constexpr (DUO) tc_commit_2sm(smem_u32(empty_bar + stage));   // frees this stage in both CTAs
           else tc_commit(smem_u32(empty_bar + stage));  // frees the smem stage once these MMAs retire
@@ -238,6 +247,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float2 lnrs = make_float2(1.0f, 0.0f);             // folded LayerNorm: (rstd, -mean * rstd) of this thread's row,
       if constexpr (MODE == 3) {                         // fetched before blocking on the accumulator
         if (m < p.M && sub < chunks) lnrs = ln_row_scale(ep.ln_stats, m, ep.ln_chunks, p.K, ep.ln_eps);
+      }
+      uint4 res[4];                                      // MODE 4: residual of this thread's row, 32 columns of a chunk
+      auto fetch_residual = [&](int c) {
+        const int nb = n_blk * p.block_n + c * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          res[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (m < p.M && nb + j * 8 + 8 <= p.N)
+            res[j] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(ep.residual) + m * ep.ldr + nb + j * 8);
+        }
+      };
+      if constexpr (MODE == 4) {
+        if (sub < chunks) fetch_residual(sub);
       }
       mbar_wait(smem_u32(tmem_full + as), aphase);
       tc_fence_after();
@@ -288,7 +310,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n = n0 + j * 8;
             float* w = v + jj * 8;
             uint4 q;
-            if (gelu_only && n + 8 <= p.N) {
+            if constexpr (MODE == 4) {
+              // fc2 path: (acc + bias) * gamma + residual; columns past N (tile padding, N % 8 == 0) are never stored
+              if (n + 8 <= p.N) {
+                const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n), b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
+                const float4 g0 = *reinterpret_cast<const float4*>(vec_gamma + n), g1 = *reinterpret_cast<const float4*>(vec_gamma + n + 4);
+                const float2 r0 = unpack2<T>(res[j].x), r1 = unpack2<T>(res[j].y), r2 = unpack2<T>(res[j].z), r3 = unpack2<T>(res[j].w);
+                q.x = pack2<T>(fmaf(w[0] + b0.x, g0.x, r0.x), fmaf(w[1] + b0.y, g0.y, r0.y));
+                q.y = pack2<T>(fmaf(w[2] + b0.z, g0.z, r1.x), fmaf(w[3] + b0.w, g0.w, r1.y));
+                q.z = pack2<T>(fmaf(w[4] + b1.x, g1.x, r2.x), fmaf(w[5] + b1.y, g1.y, r2.y));
+                q.w = pack2<T>(fmaf(w[6] + b1.z, g1.z, r3.x), fmaf(w[7] + b1.w, g1.w, r3.y));
+              } else {
+                q = make_uint4(0u, 0u, 0u, 0u);
+              }
+            } else if (gelu_only && n + 8 <= p.N) {
               // fc1 fast path: bias + GELU in packed fp16 arithmetic
               if constexpr (MODE == 3)
                 q = ln_bias_gelu_pack8<T>(w, lnrs.x, lnrs.y, *reinterpret_cast<const float4*>(vec_gamma + n),
@@ -343,6 +378,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         if (!vec_ok) continue;
+        if constexpr (MODE == 4) {
+          if (c + 4 < chunks) fetch_residual(c + 4);     // in flight during phase B and the next chunk's TMEM loads
+        }
         __syncwarp();
         if (p.debug == 2) { __syncwarp(); continue; }
         // ---- phase B ----
@@ -467,20 +505,33 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   Params p{};
   p.M = M; p.N = (int)N; p.K = (int)K;
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, (int)N, sms);
-  GCV_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "block_n must be a multiple of 32 in [32,256]");
+  GCV_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && (p.block_n <= 256 || p.block_n == 384),
+              "block_n must be a multiple of 32 in [32,256], or 384");
   p.tiles_m = (int)((M + BM - 1) / BM);
   p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
   // DUO (cta_group::2 pairs) for the large contractions: they are shared-memory / L2 bandwidth bound with one CTA per
   // 128 x block_n tile.  GCV_GEMM_DUO=0 disables it (A/B timing).
   static int duo_env = -1;
   if (duo_env < 0) { const char* e = getenv("GCV_GEMM_DUO"); duo_env = e ? atoi(e) : 1; }
+  // Wide pair tiles (256 x 384 as two N=192 MMAs) for the large-K, N = 384k contractions (ConvNeXt fc2 / downsample):
+  // A -- the big operand there -- is then fetched once per 384 instead of once per 128 output columns, which is what
+  // bounds these GEMMs (L2 -> SM bandwidth).  One TMEM accumulator stage (384 of 512 columns).  GCV_GEMM_WIDE=0 disables.
+  static int wide_env = -1;
+  if (wide_env < 0) { const char* e = getenv("GCV_GEMM_WIDE"); wide_env = e ? atoi(e) : 1; }
+  if (force_block_n <= 0 && wide_env && duo_env && N % 384 == 0 && K >= 512 && p.tiles_m >= 2 * sms) {
+    p.block_n = 384;
+    p.tiles_n = (int)(N / 384);
+  }
   const bool duo = duo_env && p.tiles_m >= 2 && K >= 256 && p.block_n >= 64 && (int64_t)p.tiles_m * p.tiles_n >= 2 * sms;
+  GCV_REQUIRE(p.block_n <= 256 || duo, "block_n = 384 needs the paired (cta_group::2) mode");
+  p.n_sub = p.block_n > 256 ? 2 : 1;
+  p.mma_n = p.block_n / p.n_sub;
   const int stage_bytes = BM * BK * 2 + (duo ? p.block_n / 2 : p.block_n) * BK * 2;
   p.acc_stages = 512 / p.block_n;
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
   p.num_stages = kTileSmem / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
-  p.idesc = umma_idesc_f16(dtype == GCV_BF16, duo ? 2 * BM : BM, p.block_n);
+  p.idesc = umma_idesc_f16(dtype == GCV_BF16, duo ? 2 * BM : BM, p.mma_n);
   p.ep = *ep;
   {
     static int dbg = -1;
@@ -501,7 +552,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dtype, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map(&mb, dtype, B, N, K, ldb, duo ? p.block_n / 2 : p.block_n);
+  rc = make_map(&mb, dtype, B, N, K, ldb, duo ? p.mma_n / 2 : p.mma_n);
   if (rc) return rc;
 
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
@@ -509,6 +560,9 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   if (duo) grid &= ~1;
   int mode = !p.vec_ok ? 2
              : (p.vec_smem && ep->act == GCV_ACT_GELU && ep->bias && !ep->gamma && !ep->residual) ? 1 : 0;
+  if (mode == 0 && p.vec_smem && ep->act == GCV_ACT_NONE && ep->bias && ep->gamma && ep->residual &&
+      ep->store == GCV_STORE_ROWS && N % 8 == 0)
+    mode = 4;
   if (ep->ln_stats) {
     GCV_REQUIRE(mode == 1 && ep->ln_colsum && ep->ln_chunks > 0 && N % 8 == 0,
                 "tcgen05 GEMM: the folded LayerNorm needs bias + GELU, a 16-bit row-major output and N %% 8 == 0, N <= %d",
@@ -516,7 +570,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
     mode = 3;
   }
   cudaError_t le = cudaSuccess;
-  static bool attr_set[2][4][2] = {};
+  static bool attr_set[2][5][2] = {};
   bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode][duo ? 1 : 0];
   auto launch = [&](auto kernel) {
     if (!attr_done) {
@@ -548,11 +602,13 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
       if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, true>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, true>);
       else if (mode == 3) launch(gemm_tcgen05_kernel<__nv_bfloat16, 3, true>);
+      else if (mode == 4) launch(gemm_tcgen05_kernel<__nv_bfloat16, 4, true>);
       else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, true>);
     } else {
       if (mode == 0) launch(gemm_tcgen05_kernel<__nv_bfloat16, 0, false>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__nv_bfloat16, 1, false>);
       else if (mode == 3) launch(gemm_tcgen05_kernel<__nv_bfloat16, 3, false>);
+      else if (mode == 4) launch(gemm_tcgen05_kernel<__nv_bfloat16, 4, false>);
       else launch(gemm_tcgen05_kernel<__nv_bfloat16, 2, false>);
     }
   } else {
@@ -560,11 +616,13 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
       if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, true>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, true>);
       else if (mode == 3) launch(gemm_tcgen05_kernel<__half, 3, true>);
+      else if (mode == 4) launch(gemm_tcgen05_kernel<__half, 4, true>);
       else launch(gemm_tcgen05_kernel<__half, 2, true>);
     } else {
       if (mode == 0) launch(gemm_tcgen05_kernel<__half, 0, false>);
       else if (mode == 1) launch(gemm_tcgen05_kernel<__half, 1, false>);
       else if (mode == 3) launch(gemm_tcgen05_kernel<__half, 3, false>);
+      else if (mode == 4) launch(gemm_tcgen05_kernel<__half, 4, false>);
       else launch(gemm_tcgen05_kernel<__half, 2, false>);
     }
   }

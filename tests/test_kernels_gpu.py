@@ -49,6 +49,26 @@ def test_gemm_tcgen05_plain(shape, dtype):
     _close(d, a.float() @ b.float().t(), 1e-4, f"tcgen05 {shape}")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(128 * 300 + 7, 384, 1536), (128 * 296, 768, 512), (128 * 311 + 100, 384, 768)])
+def test_gemm_tcgen05_wide_pair_tiles(shape, dtype):
+    """Large-K, N = 384k contractions run as 256 x 384 cta_group::2 tiles (two N=192 MMAs, one TMEM stage)."""
+    L = _lib()
+    M, N, K = shape
+    a, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias, gamma = _rand(N, seed=3, scale=0.3), _rand(N, seed=4).abs()
+    res = _rand(M, N, dtype=dtype, seed=5)
+    want = res.float() + gamma * (a.float() @ b.float().t() + bias)
+    d = res.clone()
+    L.gemm(a, b, d, M, N, K, bias=bias, gamma=gamma, residual=d, ldr=N)
+    torch.cuda.synchronize()
+    _close(d, want, TOL[dtype], f"wide tiles {shape}")
+    d32 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.gemm(a, b, d32, M, N, K, out_f32=True)
+    torch.cuda.synchronize()
+    _close(d32, a.float() @ b.float().t(), 1e-4, f"wide tiles fp32 out {shape}")
+
+
 @pytest.mark.parametrize("block_n", [32, 64, 96, 128, 192, 256])
 def test_gemm_tcgen05_every_tile_width(block_n):
     L = _lib()
