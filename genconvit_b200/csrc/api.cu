@@ -48,6 +48,12 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
                  float* val_out, cudaStream_t stream);
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
+int swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C, int heads,
+                          int shift, cudaStream_t stream);
+int swin_patch_merge(int dtype, const void* x, void* out, int B, int res, int C, cudaStream_t stream);
+int mean_tokens(int dtype, const void* x, void* y, int B, int L, int C, cudaStream_t stream);
+int preprocess_frames(const uint8_t* x, float* y, int N, int H, int W, const float* mean3, const float* std3,
+                      cudaStream_t stream);
 bool mlp_fused_supported(int dtype, int C);
 int mlp_fused_trace(long long* out64);
 int mlp_fused(int dtype, const void* y, const float* ln_stats, float ln_eps, const void* w1, const float* b1,
@@ -171,6 +177,21 @@ int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const 
                        int CI, int CO, void* stream) {
   return convt2x2_small(dtype, x, y, w, bias, act, B, H, W, CI, CO, S(stream));
 }
+int gcv_swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C,
+                              int heads, int shift, void* stream) {
+  return swin_window_attention(dtype, qkv, out, bias_table, B, res, C, heads, shift, S(stream));
+}
+int gcv_swin_patch_merge(int dtype, const void* x, void* out, int B, int res, int C, void* stream) {
+  return swin_patch_merge(dtype, x, out, B, res, C, S(stream));
+}
+int gcv_mean_tokens(int dtype, const void* x, void* y, int B, int L, int C, void* stream) {
+  return mean_tokens(dtype, x, y, B, L, C, S(stream));
+}
+int gcv_preprocess_frames(const uint8_t* x, float* y, int N, int H, int W, const float* mean3, const float* std3,
+                          void* stream) {
+  return preprocess_frames(x, y, N, H, W, mean3, std3, S(stream));
+}
+
 int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video, float* mean_out,
                      int32_t* cls_out, float* val_out, void* stream) {
   return score_videos(logits, n_nets, n_frames, frames_per_video, mean_out, cls_out, val_out, S(stream));

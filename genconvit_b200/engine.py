@@ -164,6 +164,91 @@ class PackedConvNeXt:
         return out
 
 
+SWIN_DEPTHS = (2, 2, 6, 2)
+SWIN_HEADS = (3, 6, 12, 24)
+
+
+class PackedSwin:
+    """Kernel-layout copy of a timm-style swin_tiny_patch4_window7_224 ``state_dict`` (prefix-free keys) and its
+    forward on the CUDA kernels.  The reference builds this network as ``self.embedder``
+    (model/genconvit_ed.py:69, model/genconvit_vae.py:96) and hands it to HybridEmbed, but no GenConViT logit depends
+    on it; it is provided as the standalone callable ``model.embedder(x)``.
+    Arithmetic contract: oracle/backbones.py swin_forward (pinned against torchvision)."""
+
+    def __init__(self, sd, dev, dt):
+        self.dev, self.dt = dev, dt
+        w = sd["patch_embed.proj.weight"]                         # [96,3,4,4] -> [96, (kh,kw,c)]
+        self.pe_w = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], 48), dev, dt)
+        self.pe_b = _f32(sd["patch_embed.proj.bias"], dev)
+        self.pe_ln = (_f32(sd["patch_embed.norm.weight"], dev), _f32(sd["patch_embed.norm.bias"], dev))
+        self.layers = []
+        for l, depth in enumerate(SWIN_DEPTHS):
+            blocks = []
+            for k in range(depth):
+                q = f"layers.{l}.blocks.{k}."
+                blocks.append(dict(
+                    n1=(_f32(sd[q + "norm1.weight"], dev), _f32(sd[q + "norm1.bias"], dev)),
+                    n2=(_f32(sd[q + "norm2.weight"], dev), _f32(sd[q + "norm2.bias"], dev)),
+                    qkv_w=_cd(sd[q + "attn.qkv.weight"], dev, dt), qkv_b=_f32(sd[q + "attn.qkv.bias"], dev),
+                    proj_w=_cd(sd[q + "attn.proj.weight"], dev, dt), proj_b=_f32(sd[q + "attn.proj.bias"], dev),
+                    table=_f32(sd[q + "attn.relative_position_bias_table"], dev),
+                    fc1_w=_cd(sd[q + "mlp.fc1.weight"], dev, dt), fc1_b=_f32(sd[q + "mlp.fc1.bias"], dev),
+                    fc2_w=_cd(sd[q + "mlp.fc2.weight"], dev, dt), fc2_b=_f32(sd[q + "mlp.fc2.bias"], dev)))
+            layer = {"blocks": blocks}
+            if l < 3:
+                q = f"layers.{l}.downsample."
+                layer["merge_ln"] = (_f32(sd[q + "norm.weight"], dev), _f32(sd[q + "norm.bias"], dev))
+                layer["merge_w"] = _cd(sd[q + "reduction.weight"], dev, dt)
+            self.layers.append(layer)
+        self.norm = (_f32(sd["norm.weight"], dev), _f32(sd["norm.bias"], dev))
+        self.head_w, self.head_b = _cd(sd["head.weight"], dev, dt), _f32(sd["head.bias"], dev)
+
+    def forward_images(self, x, backend=L.GEMM_AUTO):
+        """fp32 NCHW 224x224 frames -> fp32 [N,1000] logits (timm SwinTransformer.forward)."""
+        dev, dt = self.dev, self.dt
+        n, _, hh, ww = x.shape
+        if (hh, ww) != (224, 224):
+            raise L.GcvError(f"swin_tiny_patch4_window7_224 takes 224x224 frames, got {hh}x{ww}")
+        res, c = 56, 96
+        m = n * res * res
+        a0 = _empty((m, 48), dt, dev)
+        L.stem_patchify_nchw(x, a0, n, hh, ww)
+        t = _empty((m, c), dt, dev)
+        L.gemm(a0, self.pe_w, t, m, c, 48, bias=self.pe_b, backend=backend)
+        L.layernorm_rows(t, t, self.pe_ln[0], self.pe_ln[1], 1e-5, m, c)
+        for l, layer in enumerate(self.layers):
+            heads = SWIN_HEADS[l]
+            h = _empty((m, c), dt, dev)
+            qkv = _empty((m, 3 * c), dt, dev)
+            att = _empty((m, c), dt, dev)
+            hid = _empty((m, 4 * c), dt, dev)
+            for k, blk in enumerate(layer["blocks"]):
+                shift = 0 if (k % 2 == 0 or res <= 7) else 3
+                # x = x + proj(W-MSA(norm1(x)))
+                L.layernorm_rows(t, h, blk["n1"][0], blk["n1"][1], 1e-5, m, c)
+                L.gemm(h, blk["qkv_w"], qkv, m, 3 * c, c, bias=blk["qkv_b"], backend=backend)
+                L.swin_window_attention(qkv, att, blk["table"], n, res, c, heads, shift)
+                L.gemm(att, blk["proj_w"], t, m, c, c, bias=blk["proj_b"], residual=t, ldr=c, backend=backend)
+                # x = x + fc2(GELU(fc1(norm2(x))))
+                L.layernorm_rows(t, h, blk["n2"][0], blk["n2"][1], 1e-5, m, c)
+                L.gemm(h, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)
+                L.gemm(hid, blk["fc2_w"], t, m, c, 4 * c, bias=blk["fc2_b"], residual=t, ldr=c, backend=backend)
+            if l < 3:
+                m2 = m // 4
+                mg = _empty((m2, 4 * c), dt, dev)
+                L.swin_patch_merge(t, mg, n, res, c)
+                L.layernorm_rows(mg, mg, layer["merge_ln"][0], layer["merge_ln"][1], 1e-5, m2, 4 * c)
+                t = _empty((m2, 2 * c), dt, dev)
+                L.gemm(mg, layer["merge_w"], t, m2, 2 * c, 4 * c, backend=backend)
+                m, res, c = m2, res // 2, 2 * c
+        L.layernorm_rows(t, t, self.norm[0], self.norm[1], 1e-5, m, c)
+        pooled = _empty((n, c), dt, dev)
+        L.mean_tokens(t, pooled, n, res * res, c)
+        out = _empty((n, 1000), torch.float32, dev)
+        L.gemm(pooled, self.head_w, out, n, 1000, c, bias=self.head_b, out_f32=dt != torch.float32, backend=backend)
+        return out
+
+
 def _pack_conv3x3(w, dev, dt):
     """[Co,Ci,3,3] -> [Co, (kh,kw,ci)] matching gcv_im2col3x3's column order."""
     return _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), dev, dt)

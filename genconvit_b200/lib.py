@@ -25,6 +25,7 @@ EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
     "gcv_im2col3x3", "gcv_maxpool2", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
 
@@ -77,6 +78,10 @@ def load():
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_score_videos.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.gcv_swin_window_attention.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.gcv_swin_patch_merge.argtypes = [i32, vp, vp, i32, i32, i32, vp]
+    lib.gcv_mean_tokens.argtypes = [i32, vp, vp, i32, i32, i32, vp]
+    lib.gcv_preprocess_frames.argtypes = [vp, vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("gcv_last_error",):
@@ -267,6 +272,31 @@ def resize2x_to_nchw(x, y, B, H, W, Cc):
 def nhwc_to_nchw_f32(x, y, B, H, W, Cc):
     _run("nhwc_to_nchw_f32", B * H * W * Cc * (x.element_size() + 4.0), lambda: load().gcv_nhwc_to_nchw_f32(
         DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
+
+
+def swin_window_attention(qkv, out, bias_table, B, res, c, heads, shift):
+    _run("swin_window_attention", 4.0 * B * res * res * 49 * c, lambda: load().gcv_swin_window_attention(
+        DTYPE_CODE[qkv.dtype], _p(qkv), _p(out), _p(bias_table), B, res, c, heads, shift, _stream()),
+        f"B{B} res{res} C{c} shift{shift}")
+
+
+def swin_patch_merge(x, out, B, res, c):
+    _run("swin_patch_merge", 2.0 * B * res * res * c * x.element_size(), lambda: load().gcv_swin_patch_merge(
+        DTYPE_CODE[x.dtype], _p(x), _p(out), B, res, c, _stream()))
+
+
+def mean_tokens(x, y, B, Lt, c):
+    _run("mean_tokens", 1.0 * B * Lt * c * x.element_size(), lambda: load().gcv_mean_tokens(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), B, Lt, c, _stream()))
+
+
+def preprocess_frames(x_u8, y, N, H, W, mean, std):
+    """uint8 NHWC device frames -> ImageNet-normalised fp32 NCHW; see gcv_preprocess_frames."""
+    require_cuda(x_u8, "preprocess_frames")
+    assert x_u8.dtype == torch.uint8 and y.dtype == torch.float32
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _run("preprocess_frames", 15.0 * N * H * W, lambda: load().gcv_preprocess_frames(
+        _p(x_u8), _p(y), N, H, W, m3, s3, _stream()))
 
 
 def score_videos(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out):

@@ -163,12 +163,14 @@ class _PatchEmbed(nn.Module):
 
 
 class SwinTransformer(nn.Module):
-    """swin_tiny_patch4_window7_224 parameter container (28.3 M parameters + index/mask buffers).
+    """swin_tiny_patch4_window7_224 (28.3 M parameters + index/mask buffers) with timm's state_dict keys.
 
-    The reference constructs it as ``embedder`` and wraps it in ``HybridEmbed``, but its
-    forward never reaches either, so no logit depends on it.  Kernels for a
-    standalone ``embedder(x)`` are SURVEY.md section 8(f) rank 2 ("next"); until they exist calling it
-    raises instead of silently running a library fallback.
+    The reference constructs it as ``embedder`` and wraps it in ``HybridEmbed``, but its GenConViT
+    forward never reaches either, so no logit depends on it.  ``embedder(x)``
+    is a standalone callable -> [N,1000] running on the CUDA kernels (engine.PackedSwin: tcgen05 GEMMs,
+    row LayerNorm, the window-attention / patch-merge kernels of csrc/swin_ops.cu).  The
+    ``relative_position_index`` / ``attn_mask`` buffers are kept for the state_dict; the kernels
+    recompute both from (window, shift, resolution), which is what defines them.
     """
 
     def __init__(self):
@@ -183,10 +185,24 @@ class SwinTransformer(nn.Module):
         self.norm = nn.LayerNorm(768)
         self.head = nn.Linear(768, 1000)
         self.num_features = 768
+        self._packed = None
+        self.compute_dtype = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
 
     def forward(self, x):
-        raise NotImplementedError(
-            "Swin-T embedder kernels are not built yet (off the GenConViT logit path; SURVEY.md section 8f rank 2)")
+        """fp32 NCHW 224x224 frames -> fp32 [N,1000] logits, on the CUDA kernels."""
+        L.require_cuda(x, "SwinTransformer.forward")
+        dt = compute_dtype_of(self, self.compute_dtype)
+        if self._packed is None or self._packed.dt != dt or self._packed.dev != x.device:
+            self._packed = engine.PackedSwin(self.state_dict(), x.device, dt)
+        return self._packed.forward_images(x.float().contiguous())
 
 
 _MODELS = {"convnext_tiny": ConvNeXt, "swin_tiny_patch4_window7_224": SwinTransformer}

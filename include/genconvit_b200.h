@@ -167,6 +167,28 @@ int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const 
 int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
 int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
 
+/* -- Swin-T embedder kernels ------------------------------------------------
+ * timm swin_tiny_patch4_window7_224 (`self.embedder`, reference model/genconvit_ed.py:69, genconvit_vae.py:96);
+ * every Linear / LayerNorm of it runs on gcv_gemm / gcv_layernorm_rows, these are the rest:
+ * gcv_swin_window_attention: W-MSA / SW-MSA core of one SwinTransformerBlock: qkv [B*res*res, 3C] (q | k | v, heads
+ *   of 32 channels) -> out [B*res*res, C] = softmax(q k^T / sqrt(32) + rel-pos bias (+ shifted-window mask)) v per
+ *   7x7 window and head; cyclic shift / window partition / reverse are index arithmetic; bias_table [169, heads].
+ * gcv_swin_patch_merge: PatchMerging gather x [B,res,res,C] -> [B,res/2,res/2,4C] in timm's (0,0),(1,0),(0,1),(1,1)
+ *   order (LayerNorm(4C) and the bias-free reduction follow as gcv_layernorm_rows + gcv_gemm).
+ * gcv_mean_tokens: x [B,L,C] -> mean over L [B,C] (the pooling before `head`).
+ */
+int gcv_swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table,
+                              int B, int res, int C, int heads, int shift, void* stream);
+int gcv_swin_patch_merge(int dtype, const void* x, void* out, int B, int res, int C, void* stream);
+int gcv_mean_tokens(int dtype, const void* x, void* y, int B, int L, int C, void* stream);
+
+/* -- frame ingest -------------------------------------------------------------
+ * model/pred_func.py:95-108 (preprocess_frame) + dataset/loader.py:63-77: uint8 NHWC frames (device) -> fp32 NCHW
+ * ((x / 255) - mean) / std, bit-identical to the reference's fp32 CPU arithmetic.  mean3 / std3: HOST float[3].
+ */
+int gcv_preprocess_frames(const uint8_t* x, float* y, int N, int H, int W, const float* mean3, const float* std3,
+                          void* stream);
+
 /* -- scoring ----------------------------------------------------------------
  * model/pred_func.py:111-131 (pred_vid after the forward + max_prediction_value),
  * batched over videos: logits [n_nets*n_frames, 2] fp32 with each net's rows

@@ -44,8 +44,21 @@ def load_genconvit(config, net, ed_weight, vae_weight, fp16, arch_type="original
 
 
 def preprocess_frame(frame):
-    """uint8 NHWC face crops -> ImageNet-normalised fp32 NCHW on ``device`` (reference :95-108)."""
-    df = torch.as_tensor(np.asarray(frame)).float().permute(0, 3, 1, 2) / 255.0
+    """uint8 NHWC face crops -> ImageNet-normalised fp32 NCHW on ``device`` (reference :95-108).
+
+    With a GPU the uint8 frames are copied as they are (a quarter of the fp32 bytes) and normalised by
+    the ``gcv_preprocess_frames`` kernel -- same fp32 operation order as the reference's per-frame CPU loop, so the
+    result is bit-identical; without one this is host pre-processing, done with torch like the reference."""
+    arr = np.ascontiguousarray(np.asarray(frame))
+    if torch.cuda.is_available() and arr.dtype == np.uint8 and arr.ndim == 4 and arr.shape[3] == 3 \
+            and (arr.shape[1] * arr.shape[2]) % 4 == 0 and arr.shape[0] > 0:
+        from genconvit_b200 import lib as L
+        n, h, w, _ = arr.shape
+        u8 = torch.from_numpy(arr).to(device, non_blocking=False)
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=device)
+        L.preprocess_frames(u8, out, n, h, w, _MEAN, _STD)
+        return out
+    df = torch.as_tensor(arr).float().permute(0, 3, 1, 2) / 255.0
     mean = torch.tensor(_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(_STD).view(1, 3, 1, 1)
     df = (df - mean) / std

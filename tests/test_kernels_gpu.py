@@ -435,3 +435,68 @@ def test_bad_arguments_return_errors_not_crashes():
         L.dwconv7_ln(x, x, x, x, x, x, 1e-6, 1, 2, 2, 10)           # C % 32 != 0
     with pytest.raises(L.GcvError):
         L.gemm(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 4), 4, 4, 8)   # CPU tensors: no fallback
+
+
+# --------------------------------------------------------------------------- Swin kernels / frame ingest
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cfg", [(2, 56, 96, 3, 0), (2, 56, 96, 3, 3), (3, 28, 192, 6, 3), (2, 14, 384, 12, 3),
+                                 (2, 14, 384, 12, 0), (5, 7, 768, 24, 0)])
+def test_swin_window_attention(cfg, dtype):
+    """softmax(q k^T / sqrt(32) + rel-pos bias + shifted-window mask) v per 7x7 window and head, with the cyclic shift,
+    window partition and reverse folded into the indexing -- vs the oracle's roll / partition / mask restatement."""
+    from oracle import backbones as OB
+    L = _lib()
+    B, res, C, heads, shift = cfg
+    qkv = _rand(B * res * res, 3 * C, dtype=dtype, seed=1)
+    table = _rand(169, heads, seed=2, scale=0.5)
+    out = torch.full((B * res * res, C), float("nan"), device=DEV, dtype=dtype)
+    L.swin_window_attention(qkv, out, table, B, res, C, heads, shift)
+    torch.cuda.synchronize()
+    # torch restatement on the same (rounded) qkv, following oracle/backbones.py swin_block / swin_window_attention
+    h = qkv.float().cpu().view(B, res, res, 3 * C)
+    if shift:
+        h = torch.roll(h, (-shift, -shift), (1, 2))
+    hw = OB._window_partition(h, 7).view(-1, 49, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = hw[0] * 32 ** -0.5, hw[1], hw[2]
+    attn = q @ k.transpose(-2, -1)
+    idx = OB.swin_relative_position_index(7)
+    attn = attn + table.cpu()[idx.view(-1)].view(49, 49, heads).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        mask = OB.swin_attn_mask(res, 7, shift)
+        nw = mask.shape[0]
+        attn = (attn.view(B, nw, heads, 49, 49) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, 49, 49)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, 7, 7, C)
+    o = OB._window_reverse(o, 7, res, res)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    _close(out.cpu(), o.reshape(B * res * res, C), TOL[dtype], f"swin attention {cfg}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_swin_patch_merge_and_mean_tokens(dtype):
+    L = _lib()
+    B, res, C = 3, 14, 192
+    x = _rand(B, res, res, C, dtype=dtype, seed=1)
+    out = torch.empty(B, res // 2, res // 2, 4 * C, device=DEV, dtype=dtype)
+    L.swin_patch_merge(x, out, B, res, C)
+    want = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    assert torch.equal(out, want)
+    y = torch.empty(B, C, device=DEV, dtype=dtype)
+    L.mean_tokens(x, y, B, res * res, C)
+    _close(y, x.float().view(B, -1, C).mean(1), TOL[dtype], "mean_tokens")
+
+
+@pytest.mark.parametrize("shape", [(1, 224, 224), (15, 224, 224), (4, 6, 10)])
+def test_preprocess_frames_bit_exact(shape):
+    """uint8 NHWC -> ((x / 255) - mean) / std fp32 NCHW: bit-identical to the reference's CPU arithmetic
+    (model/pred_func.py:95-108 + dataset/loader.py:63-77)."""
+    L = _lib()
+    N, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, generator=g)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    want = frames.float().permute(0, 3, 1, 2) / 255.0
+    want = (want - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    y = torch.full((N, 3, H, W), float("nan"), device=DEV)
+    L.preprocess_frames(frames.to(DEV), y, N, H, W, mean, std)
+    assert torch.equal(y.cpu(), want)
