@@ -102,7 +102,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   float* vec_gamma = vec_bias + kVecMaxN;
   const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem + 1023u) & ~1023u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform (see elect_one)
+  const int lane = threadIdx.x & 31;
   const uint32_t b_rows = DUO ? (uint32_t)p.mma_n >> 1 : (uint32_t)p.mma_n;     // B rows this CTA stages per MMA
   const uint32_t a_bytes = BM * BK * 2, sub_bytes = b_rows * BK * 2, b_bytes = (uint32_t)p.n_sub * sub_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -153,8 +154,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int walk_tiles = DUO ? ((p.tiles_m + 1) >> 1) * p.tiles_n : num_tiles;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = walker; tile < walk_tiles; tile += walkers) {
@@ -164,7 +165,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
           const uint32_t fb = smem_u32(full_bar + stage);
           const uint32_t sa = tiles_base + stage * stage_bytes;
-          if constexpr (DUO) {
+          if (!elect_one()) {
+            // nothing to issue
+          } else if (p.debug >= 3) {
+            // mainloop experiments (results are garbage): 3 = no A loads, 4 = no B loads, 5 = no loads at all
+            const bool ldA = p.debug == 4, ldB = p.debug == 3;
+            const uint32_t bytes = (ldA ? a_bytes : 0u) + (ldB ? b_bytes : 0u);
+            if (!DUO || leader) mbar_expect_tx(fb, DUO ? 2 * bytes : bytes);
+            if constexpr (DUO) {
+              if (ldA) tma_load_2d_2sm(sa, &tmap_a, fb, kb * BK, m_blk * BM);
+              if (ldB)
+                for (int j = 0; j < p.n_sub; ++j)
+                  tma_load_2d_2sm(sa + a_bytes + j * sub_bytes, &tmap_b, fb, kb * BK,
+                                  n_blk * p.block_n + j * p.mma_n + (int)(crank * b_rows));
+            } else {
+              if (ldA) tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
+              if (ldB) tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
+            }
+          } else if constexpr (DUO) {
             // both CTAs' loads complete on the leader's barrier, which therefore expects two stages' worth of bytes
             if (leader) mbar_expect_tx(fb, 2 * stage_bytes);
             tma_load_2d_2sm(sa, &tmap_a, fb, kb * BK, m_blk * BM);
@@ -176,13 +194,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d(sa, &tmap_a, fb, kb * BK, m_blk * BM);
             tma_load_2d(sa + a_bytes, &tmap_b, fb, kb * BK, n_blk * p.block_n);
           }
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && (!DUO || leader)) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    if (!DUO || leader) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -197,22 +216,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sa = tiles_base + stage * stage_bytes;
           const int k_left = p.K - kb * BK;
           const int kmma = k_left >= BK ? BK / 16 : (k_left + 15) / 16;
-          for (int k = 0; k < kmma; ++k) {
-            const uint64_t ad = umma_desc(sa + k * 32);
-            if constexpr (DUO) {
-              for (int j = 0; j < p.n_sub; ++j)
-                tc_mma_2sm(d_tmem + (uint32_t)(j * p.mma_n), ad, umma_desc(sa + a_bytes + j * sub_bytes + k * 32), p.idesc,
-                           (kb | k) ? 1u : 0u);
+          if (elect_one()) {
+            // descriptors advance by 32 B (= 2 in the >>4 address field) per K=16 slice
+            const uint64_t ad0 = umma_desc(sa), bd0 = umma_desc(sa + a_bytes);
+            if (kmma == BK / 16 && p.n_sub == 1) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                if constexpr (DUO) tc_mma_2sm(d_tmem, ad0 + 2 * k, bd0 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                else tc_mma(d_tmem, ad0 + 2 * k, bd0 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+              }
             } else {
-              tc_mma(d_tmem, ad, umma_desc(sa + a_bytes + k * 32), p.idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < kmma; ++k) {
+                if constexpr (DUO) {
+                  for (int j = 0; j < p.n_sub; ++j)
+                    tc_mma_2sm(d_tmem + (uint32_t)(j * p.mma_n), ad0 + 2 * k, bd0 + ((j * sub_bytes) >> 4) + 2 * k, p.idesc,
+                               (kb | k) ? 1u : 0u);
+                } else {
+                  tc_mma(d_tmem, ad0 + 2 * k, bd0 + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                }
+              }
+            }
+            if constexpr (DUO) tc_commit_2sm(smem_u32(empty_bar + stage));   // frees this stage in both CTAs
+            else tc_commit(smem_u32(empty_bar + stage));  // frees the smem stage once these MMAs retire
+            if (kb == num_kb - 1) {
+              if constexpr (DUO) tc_commit_2sm(smem_u32(tmem_full + as));      // accumulator complete, in both CTAs' TMEM
+              else tc_commit(smem_u32(tmem_full + as));        // accumulator complete
             }
           }
-          if constexpr (DUO) tc_commit_2sm(smem_u32(empty_bar + stage));   // frees this stage in both CTAs
-          else tc_commit(smem_u32(empty_bar + stage));  // frees the smem stage once these MMAs retire
+          __syncwarp();
           if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (DUO) tc_commit_2sm(smem_u32(tmem_full + as));      // accumulator complete, in both CTAs' TMEM
-        else tc_commit(smem_u32(tmem_full + as));        // accumulator complete
         if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
@@ -269,7 +302,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
         if (lane == 0) release_acc(as);
       }
-      if (p.debug == 1) {
+      if (p.debug == 1 || p.debug >= 3) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && sub < chunks) release_acc(as);
@@ -531,6 +564,11 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
   p.num_stages = kTileSmem / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  {
+    static int cap = -1;                                   // GCV_GEMM_STAGES: pipeline-depth experiments
+    if (cap < 0) { const char* e = getenv("GCV_GEMM_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && p.num_stages > cap) p.num_stages = cap;
+  }
   p.idesc = umma_idesc_f16(dtype == GCV_BF16, duo ? 2 * BM : BM, p.mma_n);
   p.ep = *ep;
   {

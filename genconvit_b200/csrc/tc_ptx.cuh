@@ -99,6 +99,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// One lane of a CONVERGED warp.  The single-thread tcgen05 / TMA instructions take their operands from uniform
+// registers: issued from `if (lane == 0)` code the compiler cannot prove the operands warp-uniform and wraps every
+// instruction in an ELECT + 5 x R2UR.BROADCAST + branch "waterfall" (measured: ~70 clk of issue per MMA, the MMA warp
+// then cannot keep the tensor pipe fed -- tools/ubench_tcgen05.cu).  Running the loop with the whole warp and
+// predicating only the instruction on elect.sync keeps descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
