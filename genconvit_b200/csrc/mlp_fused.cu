@@ -120,7 +120,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   uint8_t* h_gen = gbase + kFCtrl + K::VEC_BYTES + K::XBUF * K::X_BYTES;   // generic pointer to H0
   uint8_t* stage_gen = h_gen + 2 * K::H_BYTES + K::RING * K::SLOT;          // output staging, one 2 KB tile per warp
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (tc_ptx.cuh elect_one)
+  const int lane = threadIdx.x & 31;
   const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = my_tiles * K::NCH;            // hidden chunks this CTA processes, numbered g = 0 .. total-1
 
@@ -164,8 +165,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   // Buffer bookkeeping shared by all roles.  Tile i of this CTA uses y buffer i % XBUF for the (i / XBUF)-th time and
   // output accumulator i % OBUF for the (i / OBUF)-th time; chunk g uses S / H buffer g & 1 for the (g >> 1)-th time.
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
+    {
       int slot = 0;
       uint32_t rphase = 0;
       TR_DECL
@@ -175,11 +176,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         TR_BEGIN
         mbar_wait(smem_u32(x_empty + xb), (use & 1) ^ 1);
         TR_END(0)
-        mbar_expect_tx(smem_u32(x_full + xb), K::X_BYTES);
         const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(x_full + xb), K::X_BYTES);
 #pragma unroll 1
-        for (int kb = 0; kb < K::XKB; ++kb)
-          tma_load_2d(x_smem + xb * K::X_BYTES + kb * FBLK, &tm_y, smem_u32(x_full + xb), kb * FKB, tile * FM);
+          for (int kb = 0; kb < K::XKB; ++kb)
+            tma_load_2d(x_smem + xb * K::X_BYTES + kb * FBLK, &tm_y, smem_u32(x_full + xb), kb * FKB, tile * FM);
+        }
+        __syncwarp();
       };
       if (my_tiles > 0) issue_x(0);
 #pragma unroll 1
@@ -191,11 +195,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             TR_BEGIN
             mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
             TR_END(1)
-            mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+            if (elect_one()) {
+              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
 #pragma unroll
-            for (int kb = 0; kb < K::KB1; ++kb)
-              tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
-                          (part * K::KB1 + kb) * FKB, j * FCH);
+              for (int kb = 0; kb < K::KB1; ++kb)
+                tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
+                            (part * K::KB1 + kb) * FKB, j * FCH);
+            }
+            __syncwarp();
             if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
           // next tile's y block: a whole tile ahead with two buffers, else as soon as this tile's fc1s can retire
@@ -208,11 +215,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             TR_BEGIN
             mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
             TR_END(1)
-            mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+            if (elect_one()) {
+              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
 #pragma unroll
-            for (int kb = 0; kb < K::KB2; ++kb)
-              tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
-                          jj * FCH + (part * K::KB2 + kb) * FKB, 0);
+              for (int kb = 0; kb < K::KB2; ++kb)
+                tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
+                            jj * FCH + (part * K::KB2 + kb) * FKB, 0);
+            }
+            __syncwarp();
             if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
         }
@@ -220,8 +230,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       TR_DUMP(0)
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
+    {
       int slot = 0;
       uint32_t rphase = 0;
       TR_DECL
@@ -254,17 +264,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             tc_fence_after();
             const uint64_t da = dx0 + (uint64_t)((xb * K::X_BYTES + part * K::KB1 * FBLK) >> 4);
             const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < K::KB1; ++kb)
+              for (int kb = 0; kb < K::KB1; ++kb)
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1,
-                       (part | kb | k) ? 1u : 0u);
-            tc_commit(smem_u32(ring_empty + slot));
+                for (int k = 0; k < 2; ++k)
+                  tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1,
+                         (part | kb | k) ? 1u : 0u);
+              tc_commit(smem_u32(ring_empty + slot));
+              if (part == K::P1 - 1) {
+                tc_commit(smem_u32(s_full + b));
+                if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));      // y buffer may be refilled
+              }
+            }
+            __syncwarp();
             if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
-          tc_commit(smem_u32(s_full + b));
-          if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));      // y buffer may be refilled
         }
         if (g >= 2) {
           const int gj = g - 2, ti = gj / K::NCH, jj = gj - ti * K::NCH;
@@ -288,17 +303,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             tc_fence_after();
             const uint64_t da = dh0 + (uint64_t)((hb * K::H_BYTES + part * K::KB2 * FBLK) >> 4);
             const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < K::KB2; ++kb)
+              for (int kb = 0; kb < K::KB2; ++kb)
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                tc_mma(dout, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * C * 64 + k * 32) >> 4), p.idesc2,
-                       (jj | part | kb | k) ? 1u : 0u);
-            tc_commit(smem_u32(ring_empty + slot));
+                for (int k = 0; k < 2; ++k)
+                  tc_mma(dout, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * C * 64 + k * 32) >> 4), p.idesc2,
+                         (jj | part | kb | k) ? 1u : 0u);
+              tc_commit(smem_u32(ring_empty + slot));
+              if (part == K::P2 - 1) {
+                tc_commit(smem_u32(h_empty + hb));
+                if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
+              }
+            }
+            __syncwarp();
             if (++slot == K::RING) { slot = 0; rphase ^= 1; }
           }
-          tc_commit(smem_u32(h_empty + hb));
-          if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
         }
       }
       TR_DUMP(8)
