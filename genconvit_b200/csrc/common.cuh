@@ -140,15 +140,28 @@ __device__ __forceinline__ uint4 gelu_pack8_h2(const __half2 x0, const __half2 x
   return q;
 }
 
-// folded LayerNorm + bias + GELU on 8 fp32 accumulators: x = w * rs + (rm * colsum + bias)
+// d = a * b + c on two fp32 lanes with one FFMA2 (fma.rn.f32x2: same rounding as two fmaf, half the issue slots)
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
+// folded LayerNorm + bias + GELU on 8 fp32 accumulators: x = w * rs + (rm * colsum + bias), two columns per FFMA2
 template <typename T>
 __device__ __forceinline__ uint4 ln_bias_gelu_pack8(const float* w, const float rs, const float rm, const float4 s0,
                                                     const float4 s1, const float4 b0, const float4 b1) {
-  return gelu_pack8_h2<T>(
-      __floats2half2_rn(fmaf(w[0], rs, fmaf(rm, s0.x, b0.x)), fmaf(w[1], rs, fmaf(rm, s0.y, b0.y))),
-      __floats2half2_rn(fmaf(w[2], rs, fmaf(rm, s0.z, b0.z)), fmaf(w[3], rs, fmaf(rm, s0.w, b0.w))),
-      __floats2half2_rn(fmaf(w[4], rs, fmaf(rm, s1.x, b1.x)), fmaf(w[5], rs, fmaf(rm, s1.y, b1.y))),
-      __floats2half2_rn(fmaf(w[6], rs, fmaf(rm, s1.z, b1.z)), fmaf(w[7], rs, fmaf(rm, s1.w, b1.w))));
+  const float2 rs2 = make_float2(rs, rs), rm2 = make_float2(rm, rm);
+  const float2 x0 = fma2(make_float2(w[0], w[1]), rs2, fma2(rm2, make_float2(s0.x, s0.y), make_float2(b0.x, b0.y)));
+  const float2 x1 = fma2(make_float2(w[2], w[3]), rs2, fma2(rm2, make_float2(s0.z, s0.w), make_float2(b0.z, b0.w)));
+  const float2 x2 = fma2(make_float2(w[4], w[5]), rs2, fma2(rm2, make_float2(s1.x, s1.y), make_float2(b1.x, b1.y)));
+  const float2 x3 = fma2(make_float2(w[6], w[7]), rs2, fma2(rm2, make_float2(s1.z, s1.w), make_float2(b1.z, b1.w)));
+  return gelu_pack8_h2<T>(__floats2half2_rn(x0.x, x0.y), __floats2half2_rn(x1.x, x1.y), __floats2half2_rn(x2.x, x2.y),
+                          __floats2half2_rn(x3.x, x3.y));
 }
 
 // bias + GELU on 8 fp32 accumulators -> 8 packed 16-bit outputs (T = __half or __nv_bfloat16)

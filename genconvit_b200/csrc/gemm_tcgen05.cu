@@ -35,8 +35,8 @@ constexpr int kTileSmem = 160 * 1024;            // 227 KB budget minus control 
 constexpr int kVecMaxN = 3072;                   // bias / layer-scale vectors up to this N are staged in smem
 constexpr int kVecSmem = 2 * kVecMaxN * 4;
 constexpr int kCtrlSmem = 1024;
-constexpr int kStageRow = 80;                            // staged row: 32 x 16-bit + 16 B pad (conflict-free v4 access)
-constexpr int kStageWarp = 32 * kStageRow;               // per epilogue warp: 32 rows x 32 columns
+constexpr int kStageRow = 64;                            // staged row: 32 x 16-bit, 16-byte pieces XOR-swizzled (TMA SWIZZLE_64B)
+constexpr int kStageWarp = 32 * kStageRow;               // per epilogue warp: 32 rows x 32 columns = one TMA store box
 constexpr int kStageSmem = kEpiWarps * kStageWarp;
 constexpr int kDynSmem = kCtrlSmem + kStageSmem + kVecSmem + 1024 + kTileSmem;   // +1024 alignment slack
 constexpr uint32_t kTmemCols = 512;
@@ -50,6 +50,7 @@ struct Params {
   uint32_t idesc;
   int vec_ok;          // epilogue may use 16-byte row-chunk loads/stores
   int vec_smem;        // bias / gamma are staged in shared memory (N <= kVecMaxN)
+  int tma_store;       // row-major 16-bit output leaves through TMA stores (tmap_d) instead of per-lane st.global
   int debug;           // profiling knob (GCV_DEBUG): 1 = epilogue skips all work, 2 = skips stores
   gcv_epilogue ep;
 };
@@ -89,8 +90,10 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
 template <typename T, int MODE, bool DUO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    void* D, const Params p) {
-  extern __shared__ uint8_t smem_raw[];
+                    const __grid_constant__ CUtensorMap tmap_d, void* D, const Params p) {
+  extern __shared__ uint8_t smem_dyn[];
+  // 1024-byte aligned base: TMA / UMMA swizzle atoms (operand stages, the epilogue's store boxes)
+  uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   // control block: barriers + TMEM base pointer
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -100,7 +103,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* stage_base = smem_raw + kCtrlSmem;            // epilogue staging, kStageWarp bytes per warp
   float* vec_bias = reinterpret_cast<float*>(smem_raw + kCtrlSmem + kStageSmem);   // [kVecMaxN] bias, then gamma
   float* vec_gamma = vec_bias + kVecMaxN;
-  const uint32_t tiles_base = (smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem + 1023u) & ~1023u;
+  const uint32_t tiles_base = smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform (see elect_one)
   const int lane = threadIdx.x & 31;
@@ -167,7 +170,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sa = tiles_base + stage * stage_bytes;
           if (!elect_one()) {
             // nothing to issue
-          } else if (p.debug >= 3) {
+          } else if (p.debug >= 3 && p.debug <= 5) {
             // mainloop experiments (results are garbage): 3 = no A loads, 4 = no B loads, 5 = no loads at all
             const bool ldA = p.debug == 4, ldB = p.debug == 3;
             const uint32_t bytes = (ldA ? a_bytes : 0u) + (ldB ? b_bytes : 0u);
@@ -302,7 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
         if (lane == 0) release_acc(as);
       }
-      if (p.debug == 1 || p.debug >= 3) {
+      if (p.debug == 1 || (p.debug >= 3 && p.debug <= 5)) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && sub < chunks) release_acc(as);
@@ -310,6 +313,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int c = sub; c < chunks; c += 4) {
         const int n0 = n_blk * p.block_n + c * 32;
+        if (p.tma_store) {                               // the previous store of this warp must have drained the staging tile
+          if (elect_one()) tma_store_wait_read();
+          __syncwarp();
+        }
         // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 576-thread CTA
         // leaves 96 registers per thread)
 #pragma unroll
@@ -326,6 +333,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_before();                           // all TMEM reads of this tile by this warp are done:
             __syncwarp();                                // hand the accumulator stage back to the MMA warp early
             if (lane == 0) release_acc(as);
+          }
+          if (p.debug == 6) {                            // experiment: TMEM drain only
+            if (v[0] == 123.456f) *reinterpret_cast<float*>(my_stage) = v[5];
+            continue;
           }
           if (!vec_ok) {
             if (m < p.M) {
@@ -349,10 +360,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n), b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
                 const float4 g0 = *reinterpret_cast<const float4*>(vec_gamma + n), g1 = *reinterpret_cast<const float4*>(vec_gamma + n + 4);
                 const float2 r0 = unpack2<T>(res[j].x), r1 = unpack2<T>(res[j].y), r2 = unpack2<T>(res[j].z), r3 = unpack2<T>(res[j].w);
-                q.x = pack2<T>(fmaf(w[0] + b0.x, g0.x, r0.x), fmaf(w[1] + b0.y, g0.y, r0.y));
-                q.y = pack2<T>(fmaf(w[2] + b0.z, g0.z, r1.x), fmaf(w[3] + b0.w, g0.w, r1.y));
-                q.z = pack2<T>(fmaf(w[4] + b1.x, g1.x, r2.x), fmaf(w[5] + b1.y, g1.y, r2.y));
-                q.w = pack2<T>(fmaf(w[6] + b1.z, g1.z, r3.x), fmaf(w[7] + b1.w, g1.w, r3.y));
+                // (w + b) * g + r as w * g + (b * g + r): two FFMA2 per column pair
+                const float2 y0 = fma2(make_float2(w[0], w[1]), make_float2(g0.x, g0.y), fma2(make_float2(b0.x, b0.y), make_float2(g0.x, g0.y), r0));
+                const float2 y1 = fma2(make_float2(w[2], w[3]), make_float2(g0.z, g0.w), fma2(make_float2(b0.z, b0.w), make_float2(g0.z, g0.w), r1));
+                const float2 y2 = fma2(make_float2(w[4], w[5]), make_float2(g1.x, g1.y), fma2(make_float2(b1.x, b1.y), make_float2(g1.x, g1.y), r2));
+                const float2 y3 = fma2(make_float2(w[6], w[7]), make_float2(g1.z, g1.w), fma2(make_float2(b1.z, b1.w), make_float2(g1.z, g1.w), r3));
+                q.x = pack2<T>(y0.x, y0.y); q.y = pack2<T>(y1.x, y1.y); q.z = pack2<T>(y2.x, y2.y); q.w = pack2<T>(y3.x, y3.y);
               } else {
                 q = make_uint4(0u, 0u, 0u, 0u);
               }
@@ -407,12 +420,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               q.x = pack2<T>(w[0], w[1]); q.y = pack2<T>(w[2], w[3]);
               q.z = pack2<T>(w[4], w[5]); q.w = pack2<T>(w[6], w[7]);
             }
-            *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + j * 16) = q;
+            *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + ((j ^ ((lane >> 1) & 3)) << 4)) = q;
           }
         }
-        if (!vec_ok) continue;
+        if (!vec_ok || p.debug == 6) continue;
         if constexpr (MODE == 4) {
           if (c + 4 < chunks) fetch_residual(c + 4);     // in flight during phase B and the next chunk's TMEM loads
+        }
+        if (p.tma_store) {
+          // ---- phase B, TMA form: the 32 x 32 staged tile is one bulk tensor store (rows / columns past M / N are clipped)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (p.debug != 2 && p.debug != 7 && elect_one()) {
+            tma_store_2d(&tmap_d, smem_u32(my_stage), n0, (int)m_warp);
+            tma_store_commit();
+          }
+          __syncwarp();
+          continue;
         }
         __syncwarp();
         if (p.debug == 2) { __syncwarp(); continue; }
@@ -425,7 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int row = i * 8 + (lane >> 2);
             const int64_t mm = m_warp + row;
             if (mm < p.M) {
-              const uint4 q = *reinterpret_cast<const uint4*>(my_stage + row * kStageRow + piece * 16);
+              const uint4 q = *reinterpret_cast<const uint4*>(my_stage + row * kStageRow + ((piece ^ ((row >> 1) & 3)) << 4));
               int64_t off;
               if (ep.store == GCV_STORE_PIXEL_SHUFFLE2) {
                 const int ij = n / ep.ps_co, co = n - ij * ep.ps_co;
@@ -437,12 +461,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               } else {
                 off = mm * ep.ldd + n;
               }
-              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(D) + off) = q;
+              if (p.debug != 7 || q.x == 0x12345678u)      // 7: everything but the global store itself
+                *reinterpret_cast<uint4*>(reinterpret_cast<T*>(D) + off) = q;
             }
           }
         }
         __syncwarp();                                    // staging tile is reused by the next chunk
       }
+    }
+    if (p.tma_store) {                                   // shared memory must outlive the last bulk stores' reads
+      if (elect_one()) tma_store_wait_read();
+      __syncwarp();
     }
   }
 
@@ -476,7 +505,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows,
+             int box_cols = BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not resolvable (no CUDA driver?)");
@@ -484,11 +514,11 @@ int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_
   }
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == GCV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld k=%lld ld=%lld box_rows=%d)", (int)r,
               (long long)rows, (long long)k, (long long)ld, box_rows);
@@ -592,6 +622,16 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   if (rc) return rc;
   rc = make_map(&mb, dtype, B, N, K, ldb, duo ? p.mma_n / 2 : p.mma_n);
   if (rc) return rc;
+  // row-major 16-bit outputs leave through TMA stores: one 32 x 32 box per epilogue warp and chunk.  GCV_GEMM_TMA_STORE=0
+  // keeps the per-lane st.global path (A/B timing).
+  static int tst_env = -1;
+  if (tst_env < 0) { const char* e = getenv("GCV_GEMM_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
+  p.tma_store = (tst_env && p.vec_ok && ep->store == GCV_STORE_ROWS && N % 8 == 0) ? 1 : 0;
+  CUtensorMap md = ma;
+  if (p.tma_store) {
+    rc = make_map(&md, dtype, D, M, N, ep->ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
 
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
   int grid = (int)(tiles < sms ? tiles : sms);
@@ -617,7 +657,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
       attr_done = true;
     }
     if (!duo) {
-      kernel<<<grid, kThreads, kDynSmem, stream>>>(ma, mb, D, p);
+      kernel<<<grid, kThreads, kDynSmem, stream>>>(ma, mb, md, D, p);
       le = cudaGetLastError();
     } else {
       cudaLaunchConfig_t cfg{};
@@ -632,7 +672,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, D, p);
+      le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, md, D, p);
     }
   };
   if (dtype == GCV_BF16) {
