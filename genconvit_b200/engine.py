@@ -311,6 +311,12 @@ class PackedED:
         L.conv3x3_first(x, e, self.enc0_w, self.enc0_b, 1, L.ACT_RELU, True, n, hh, ww)
         for wt, bias in self.enc:
             co = wt.shape[0]
+            if (c, co) == (16, 32) and dt != torch.float32 and h % 2 == 0 and w % 2 == 0:
+                # the widest layer (112 x 112 pixels per frame): direct tensor-core conv + ReLU + pool, no im2col matrix
+                nxt = _empty((n * (h // 2) * (w // 2), co), dt, dev)
+                L.conv3x3_c16(e, nxt, wt, bias, 1, L.ACT_RELU, True, n, h, w)
+                e, h, w, c = nxt, h // 2, w // 2, co
+                continue
             a = _empty((n * h * w, 9 * c), dt, dev)
             L.im2col3x3(e, a, n, h, w, c, 1)
             full = _empty((n * h * w, co), dt, dev)
@@ -391,6 +397,11 @@ class PackedVAE:
         for wt, bias in self.enc:
             co = wt.shape[0]
             h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            if (c, co) == (16, 32) and dt != torch.float32:
+                nxt = _empty((n * h2 * w2, co), dt, dev)
+                L.conv3x3_c16(e, nxt, wt, bias, 2, L.ACT_LEAKY, False, n, h, w)
+                e, h, w, c = nxt, h2, w2, co
+                continue
             a = _empty((n * h2 * w2, 9 * c), dt, dev)
             L.im2col3x3(e, a, n, h, w, c, 2)
             e = _empty((n * h2 * w2, co), dt, dev)

@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -74,6 +74,7 @@ def load():
     lib.gcv_conv3x3_first.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_im2col3x3.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
@@ -252,6 +253,14 @@ def im2col3x3(x, a, B, H, W, Cc, stride):
     es = x.element_size()
     _run("im2col3x3", (B * H * W * Cc + 9.0 * B * (H // stride) * (W // stride) * Cc) * es, lambda: load().gcv_im2col3x3(
         DTYPE_CODE[x.dtype], _p(x), _p(a), B, H, W, Cc, stride, _stream()))
+
+
+def conv3x3_c16(x, y, w, bias, stride, act, pool, B, H, W):
+    """Direct 16 -> 32 channel 3x3 conv (+ act, + 2x2 max-pool) on the tensor cores; see gcv_conv3x3_c16."""
+    es = x.element_size()
+    _run("conv3x3_c16", (B * H * W * 16.0 + y.numel()) * es, lambda: load().gcv_conv3x3_c16(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), stride, act, 1 if pool else 0, B, H, W, _stream()),
+        f"B{B} H{H} W{W} s{stride}")
 
 
 def maxpool2(x, y, B, H, W, Cc):

@@ -150,6 +150,10 @@ int gcv_pool_ln(int dtype, const void* x, void* y, const float* w, const float* 
  *   genconvit_vae.py:16-18.  y: NHWC.
  * gcv_im2col3x3: x [B,H,W,C] -> A [B*Ho*Wo, 9C], column (kh*3+kw)*C + c, pad 1.
  * gcv_maxpool2: NHWC 2x2 s2 max-pool (genconvit_ed.py:16,20,24,28,32).
+ * gcv_conv3x3_c16: the encoders' second layer, Conv2d(16 -> 32, k3, pad 1) as a direct tensor-core
+ *   convolution (no im2col matrix): x [B,H,W,16], w [32][(kh,kw,ci)] of `dtype` (the GEMM B layout),
+ *   bias fp32 [32]; stride 1 + ReLU + fused 2x2 max-pool = genconvit_ed.py:18-20, stride 2 +
+ *   LeakyReLU (BatchNorm folded by the host) = genconvit_vae.py:19-21.  16-bit dtypes only.
  * gcv_convt2x2_small: the decoders' output layer ConvTranspose2d(16 -> 3, k2 s2) + act
  *   (genconvit_ed.py:56-57; genconvit_vae.py:77-78) as a streaming kernel: x [B,H,W,16] ->
  *   y [B,2H,2W,3]; w: fp32 [(i*2+j)*3 + co][ci] (the GEMM B layout), bias: fp32 [3].
@@ -162,6 +166,8 @@ int gcv_conv3x3_first(int dtype, const float* x, void* y, const float* w, const 
                       int stride, int act, int pool, int B, int H, int W, void* stream);
 int gcv_im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, void* stream);
 int gcv_maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
+int gcv_conv3x3_c16(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act,
+                    int pool, int B, int H, int W, void* stream);
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act,
                        int B, int H, int W, int CI, int CO, void* stream);
 int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);

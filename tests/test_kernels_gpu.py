@@ -500,3 +500,32 @@ def test_preprocess_frames_bit_exact(shape):
     y = torch.full((N, 3, H, W), float("nan"), device=DEV)
     L.preprocess_frames(frames.to(DEV), y, N, H, W, mean, std)
     assert torch.equal(y.cpu(), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 20, 28), (1, 112, 112), (2, 18, 50)])
+def test_conv3x3_c16_direct(shape, dtype):
+    """Direct 16 -> 32 conv on mma.sync vs torch conv2d (fp32) on the same 16-bit-rounded inputs:
+    stride 1 + ReLU + 2x2 max-pool (genconvit_ed.py:18-20) and stride 2 + LeakyReLU (genconvit_vae.py:19-21)."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_conv3x3
+    B, H, W = shape
+    x = _rand(B, H, W, 16, dtype=dtype, seed=1)
+    w = _rand(32, 16, 3, 3, seed=2, scale=144 ** -0.5)
+    b = _rand(32, seed=3, scale=0.1)
+    wp = _pack_conv3x3(w, DEV, dtype)
+    wr = wp.float().reshape(32, 3, 3, 16).permute(0, 3, 1, 2)          # the rounded weights the kernel sees
+    xin = x.float().permute(0, 3, 1, 2)
+    want = F.max_pool2d(F.relu(F.conv2d(xin, wr, b, padding=1)), 2).permute(0, 2, 3, 1)
+    out = torch.full((B, H // 2, W // 2, 32), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c16(x, out, wp, b, 1, L.ACT_RELU, True, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c16 s1 relu pool")
+    want = F.leaky_relu(F.conv2d(xin, wr, b, stride=2, padding=1), 0.01).permute(0, 2, 3, 1)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, Ho, Wo, 32), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c16(x, out, wp, b, 2, L.ACT_LEAKY, False, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c16 s2 leaky")
+    want = F.relu(F.conv2d(xin, wr, b, padding=1)).permute(0, 2, 3, 1)
+    out = torch.full((B, H, W, 32), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c16(x, out, wp, b, 1, L.ACT_RELU, False, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c16 s1 relu")
