@@ -56,39 +56,44 @@ conv3x3_first_kernel(const float* __restrict__ x, T* __restrict__ y, const float
         patch[c][i][j] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((b * 3 + c) * H + yy) * (int64_t)W + xx) : 0.0f;
       }
   // all NP*NP conv positions advance together so each tap's 16 weights are read once
-  float acc[NP * NP][16];
+  // output channels in pairs: one FFMA2 (fma.rn.f32x2) per tap and channel pair -- the kernel is FMA-issue bound
+  float2 acc[NP * NP][8];
 #pragma unroll
   for (int q = 0; q < NP * NP; ++q)
 #pragma unroll
-    for (int co = 0; co < 16; ++co) acc[q][co] = bs[co];
+    for (int co = 0; co < 8; ++co) acc[q][co] = make_float2(bs[2 * co], bs[2 * co + 1]);
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        float wr[16];
+        float2 wr[8];
 #pragma unroll
-        for (int co = 0; co < 16; co += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&ws[c * 9 + kh * 3 + kw][co]);
-          wr[co] = w4.x; wr[co + 1] = w4.y; wr[co + 2] = w4.z; wr[co + 3] = w4.w;
+        for (int co = 0; co < 8; co += 2) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[c * 9 + kh * 3 + kw][2 * co]);
+          wr[co] = make_float2(w4.x, w4.y); wr[co + 1] = make_float2(w4.z, w4.w);
         }
 #pragma unroll
         for (int py = 0; py < NP; ++py)
 #pragma unroll
           for (int px = 0; px < NP; ++px) {
             const float v = patch[c][py * STRIDE + kh][px * STRIDE + kw];
+            const float2 vv = make_float2(v, v);
 #pragma unroll
-            for (int co = 0; co < 16; ++co) acc[py * NP + px][co] = fmaf(v, wr[co], acc[py * NP + px][co]);
+            for (int co = 0; co < 8; ++co) acc[py * NP + px][co] = fma2(vv, wr[co], acc[py * NP + px][co]);
           }
       }
   float out[16];
 #pragma unroll
-  for (int co = 0; co < 16; ++co) {
-    float m = apply_act(acc[0][co], act);
+  for (int co = 0; co < 8; ++co) {
+    float m0 = apply_act(acc[0][co].x, act), m1 = apply_act(acc[0][co].y, act);
 #pragma unroll
-    for (int q = 1; q < NP * NP; ++q) m = fmaxf(m, apply_act(acc[q][co], act));
-    out[co] = m;
+    for (int q = 1; q < NP * NP; ++q) {
+      m0 = fmaxf(m0, apply_act(acc[q][co].x, act));
+      m1 = fmaxf(m1, apply_act(acc[q][co].y, act));
+    }
+    out[2 * co] = m0; out[2 * co + 1] = m1;
   }
   T* dst = y + idx * 16;
   store8<T>(dst, out);

@@ -126,6 +126,25 @@ __device__ __forceinline__ float2 ln_row_scale(const float* stats, int64_t m, in
   return make_float2(rstd, -mean * rstd);
 }
 
+// The same in two halves, so that the loads can be issued a tile ahead of their use (their latency then overlaps work):
+// ln_row_load fetches the partial sums (at most 8 chunks: K <= 256), ln_row_finish reduces them.
+__device__ __forceinline__ void ln_row_load(const float* stats, int64_t m, int chunks, float2 (&raw)[8]) {
+  const float2* p = reinterpret_cast<const float2*>(stats) + m * chunks;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < chunks) raw[i] = __ldg(p + i);
+}
+__device__ __forceinline__ float2 ln_row_finish(const float2 (&raw)[8], int chunks, int K, float eps) {
+  float s = 0.0f, q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < chunks) { s += raw[i].x; q += raw[i].y; }
+  const float inv = 1.0f / (float)K;
+  const float mean = s * inv;
+  const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, q * inv), 0.0f) + eps);
+  return make_float2(rstd, -mean * rstd);
+}
+
 template <typename T>
 __device__ __forceinline__ uint4 gelu_pack8_h2(const __half2 x0, const __half2 x1, const __half2 x2, const __half2 x3) {
   const __half2 g0 = gelu_fast_h2(x0), g1 = gelu_fast_h2(x1), g2 = gelu_fast_h2(x2), g3 = gelu_fast_h2(x3);

@@ -396,13 +396,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             f = unpack2<T>(rq.z); rr[4] = f.x; rr[5] = f.y;
             f = unpack2<T>(rq.w); rr[6] = f.x; rr[7] = f.y;
           }
-          w[0] = fmaf(w[0] + b0.x, g0.x, rr[0]); w[1] = fmaf(w[1] + b0.y, g0.y, rr[1]);
-          w[2] = fmaf(w[2] + b0.z, g0.z, rr[2]); w[3] = fmaf(w[3] + b0.w, g0.w, rr[3]);
-          w[4] = fmaf(w[4] + b1.x, g1.x, rr[4]); w[5] = fmaf(w[5] + b1.y, g1.y, rr[5]);
-          w[6] = fmaf(w[6] + b1.z, g1.z, rr[6]); w[7] = fmaf(w[7] + b1.w, g1.w, rr[7]);
+          // (w + b) * g + r as w * g + (b * g + r): two FFMA2 per column pair
+          const float2 y0 = fma2(make_float2(w[0], w[1]), make_float2(g0.x, g0.y), fma2(make_float2(b0.x, b0.y), make_float2(g0.x, g0.y), make_float2(rr[0], rr[1])));
+          const float2 y1 = fma2(make_float2(w[2], w[3]), make_float2(g0.z, g0.w), fma2(make_float2(b0.z, b0.w), make_float2(g0.z, g0.w), make_float2(rr[2], rr[3])));
+          const float2 y2 = fma2(make_float2(w[4], w[5]), make_float2(g1.x, g1.y), fma2(make_float2(b1.x, b1.y), make_float2(g1.x, g1.y), make_float2(rr[4], rr[5])));
+          const float2 y3 = fma2(make_float2(w[6], w[7]), make_float2(g1.z, g1.w), fma2(make_float2(b1.z, b1.w), make_float2(g1.z, g1.w), make_float2(rr[6], rr[7])));
           uint4 pk;
-          pk.x = pack2<T>(w[0], w[1]); pk.y = pack2<T>(w[2], w[3]);
-          pk.z = pack2<T>(w[4], w[5]); pk.w = pack2<T>(w[6], w[7]);
+          pk.x = pack2<T>(y0.x, y0.y); pk.y = pack2<T>(y1.x, y1.y);
+          pk.z = pack2<T>(y2.x, y2.y); pk.w = pack2<T>(y3.x, y3.y);
           *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4)) = pk;
         }
         __syncwarp();
@@ -422,23 +423,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     int pending = -1;
     int ln_ti = -1;
     float2 lnrs = make_float2(1.0f, 0.0f);   // folded LayerNorm: (rstd, -mean * rstd) of this thread's row of tile ln_ti
-    float2 ln_next = lnrs;                   // ... and of the following tile (prefetched)
+    float2 ln_raw[8];                        // partial sums of the FOLLOWING tile's row: loaded a tile ahead, reduced at the tile change
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ln_raw[i] = make_float2(0.0f, 1.0f);
 #pragma unroll 1
     for (int g = grp; g < total; g += 2) {
       const int ti = g / K::NCH, j = g - ti * K::NCH;
       const int b = grp;
       if constexpr (LN) {
-        // row statistics of tile ti: fetched while the previous tile's last chunk is still in flight
         if (ti != ln_ti) {
-          if (ln_ti >= 0) {
-            lnrs = ln_next;
-          } else {
+          if (ln_ti < 0) {
             const int64_t m = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + row;
-            lnrs = m < p.M ? ln_row_scale(p.ln_stats, m, C / 32, C, p.ln_eps) : make_float2(1.0f, 0.0f);
+            if (m < p.M) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
           }
+          lnrs = ln_row_finish(ln_raw, C / 32, C, p.ln_eps);
           ln_ti = ti;
           const int64_t mn = (int64_t)((int)blockIdx.x + (ti + 1) * (int)gridDim.x) * FM + row;
-          ln_next = mn < p.M ? ln_row_scale(p.ln_stats, mn, C / 32, C, p.ln_eps) : make_float2(1.0f, 0.0f);
+          if (mn < p.M) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
         }
       }
       const uint32_t n_use = (uint32_t)(g >> 1);
@@ -491,7 +492,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       // The tile's output accumulator is complete only after the OTHER group's last chunk went through fc2, so this
       // warp drains tile ti one chunk late (after its first chunk of the next tile) instead of idling on o_full.
       if (pending >= 0) { drain_output(pending); pending = -1; }
-      if ((g + 2) / K::NCH != ti) pending = ti;       // that was this group's last chunk of tile ti
+      if ((g + 2) / K::NCH != ti) {                   // that was this group's last chunk of tile ti
+        pending = ti;
+        // the drain reads the tile's residual rows from HBM: pull this warp's 32 rows into L2 a chunk ahead
+        const int64_t m_warp = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + q * 32;
+        const uint8_t* rbase = reinterpret_cast<const uint8_t*>(xg + m_warp * C);
+        const int64_t rbytes = (p.M - m_warp < 32 ? (p.M - m_warp > 0 ? p.M - m_warp : 0) : 32) * (int64_t)(C * 2);
+#pragma unroll
+        for (int i = 0; i < (32 * C * 2) / (128 * 32); ++i) {
+          const int64_t off = (int64_t)(i * 32 + lane) * 128;
+          if (off < rbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + off));
+        }
+      }
     }
     if (pending >= 0) drain_output(pending);
     if (lane == 0 && warp == 2) { TR_DUMP(16) }
