@@ -530,7 +530,9 @@ int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_
 int pick_block_n(int64_t M, int N, int sms) {
   // Largest tile that still gives every SM work; N tiles must be multiples of 32 (epilogue chunk) <= 256.
   // 256 and 128 give every epilogue warp the same number of 32-column chunks (4 warps per lane quarter)
-  const int cands[] = {256, 128, 192, 96, 64, 32};
+  // (measured after the warp-uniform issue fix: for N = 384 two 192-wide tiles with two TMEM stages beat both 3 x 128
+  // and the single-stage 384-wide pair tile by ~12 %)
+  const int cands[] = {256, 192, 128, 96, 64, 32};
   const int64_t tiles_m = (M + BM - 1) / BM;
   int best = 32;
   for (int c : cands) {
@@ -580,7 +582,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   // A -- the big operand there -- is then fetched once per 384 instead of once per 128 output columns, which is what
   // bounds these GEMMs (L2 -> SM bandwidth).  One TMEM accumulator stage (384 of 512 columns).  GCV_GEMM_WIDE=0 disables.
   static int wide_env = -1;
-  if (wide_env < 0) { const char* e = getenv("GCV_GEMM_WIDE"); wide_env = e ? atoi(e) : 1; }
+  if (wide_env < 0) { const char* e = getenv("GCV_GEMM_WIDE"); wide_env = e ? atoi(e) : 0; }   // off: its single accumulator stage serialises mainloop and epilogue
   if (force_block_n <= 0 && wide_env && duo_env && N % 384 == 0 && K >= 512 && p.tiles_m >= 2 * sms) {
     p.block_n = 384;
     p.tiles_n = (int)(N / 384);

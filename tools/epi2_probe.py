@@ -27,3 +27,8 @@ timed("fc2 bias+gamma+res", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b2, gam
 timed("fc2 plain", lambda: L.gemm(hid, w2, x, M, C, 4 * C), fl)
 timed("fc2 plain bn256", lambda: L.gemm(hid, w2, x, M, C, 4 * C, backend=1256), fl)
 timed("fc2 plain bn128", lambda: L.gemm(hid, w2, x, M, C, 4 * C, backend=1128), fl)
+timed("fc2 bias+gamma+res bn192", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b2, gamma=g, residual=x, ldr=C, backend=1192), fl)
+timed("fc2 bias+gamma+res bn128", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b2, gamma=g, residual=x, ldr=C, backend=1128), fl)
+timed("fc2 bias+gamma+res bn256", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b2, gamma=g, residual=x, ldr=C, backend=1256), fl)
+timed("fc1 bias+gelu+ln bn192", lambda: L.gemm(a, w1, hid, M, 4 * C, C, bias=b1, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6, backend=1192), fl)
+timed("fc1 bias+gelu+ln bn128", lambda: L.gemm(a, w1, hid, M, 4 * C, C, bias=b1, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6, backend=1128), fl)
