@@ -26,6 +26,9 @@ FUSED_MLP = os.environ.get("GCV_NO_FUSED_MLP", "0") != "1"
 # LayerNorm folded into fc1 (weights pre-scaled by the LN weight, row statistics applied in the fc1 epilogue), so the
 # block makes no separate normalisation pass.  GCV_NO_LNFOLD=1 keeps the explicit dwconv7_ln kernel (A/B timing).
 LN_FOLD = os.environ.get("GCV_NO_LNFOLD", "0") != "1"
+# 16-bit modes: the stem (4x4 patchify + conv + LayerNorm2d) as ONE tensor-core kernel reading the frames directly.
+# GCV_NO_FUSED_STEM=1 keeps im2col + GEMM + row LayerNorm (A/B timing).
+FUSED_STEM = os.environ.get("GCV_NO_FUSED_STEM", "0") != "1"
 
 
 def _f32(t, dev):
@@ -47,6 +50,7 @@ class PackedConvNeXt:
         self.dev, self.dt = dev, dt
         w = sd["stem.0.weight"]                                   # [96,3,4,4] -> [96, (kh,kw,c)]
         self.stem_w = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], 48), dev, dt)
+        self.stem_w_oihw = _cd(w.reshape(w.shape[0], 48), dev, dt)  # [96, (c,kh,kw)]: the fused stem reads NCHW frames
         self.stem_b = _f32(sd["stem.0.bias"], dev)
         self.stem_ln = (_f32(sd["stem.1.weight"], dev), _f32(sd["stem.1.bias"], dev))
         self.stages = []
@@ -96,10 +100,21 @@ class PackedConvNeXt:
         genconvit_ed.py:82-83 / genconvit_vae.py:111-112.
         """
         dev, dt = self.dev, self.dt
-        m = a0.shape[0]
-        x = _empty((m, DIMS[0]), dt, dev)
-        L.gemm(a0, self.stem_w, x, m, DIMS[0], 48, bias=self.stem_b, backend=backend)
-        L.layernorm_rows(x, x, self.stem_ln[0], self.stem_ln[1], 1e-6, m, DIMS[0])
+        if isinstance(a0, list):
+            # 16-bit modes: a0 is a list of frame sources (tensor, nchw?, n_images, H, W), one per run of tokens; the
+            # fused stem kernel turns each straight into normalised tokens (no im2col matrix, no separate LayerNorm)
+            m = sum(n * (hh // 4) * (ww // 4) for _, _, n, hh, ww in a0)
+            x = _empty((m, DIMS[0]), dt, dev)
+            r = 0
+            for src, nchw, n, hh, ww in a0:
+                L.stem_fused(src, x[r:], self.stem_w_oihw if nchw else self.stem_w, self.stem_b, self.stem_ln[0],
+                             self.stem_ln[1], 1e-6, n, hh, ww, nchw)
+                r += n * (hh // 4) * (ww // 4)
+        else:
+            m = a0.shape[0]
+            x = _empty((m, DIMS[0]), dt, dev)
+            L.gemm(a0, self.stem_w, x, m, DIMS[0], 48, bias=self.stem_b, backend=backend)
+            L.layernorm_rows(x, x, self.stem_ln[0], self.stem_ln[1], 1e-6, m, DIMS[0])
         segs = list(segments)
         for s, st in enumerate(self.stages):
             c = DIMS[s]
@@ -157,8 +172,11 @@ class PackedConvNeXt:
     def forward_images(self, x, act=L.ACT_NONE, backend=L.GEMM_AUTO):
         """``backbone(x)`` for fp32 NCHW frames -> fp32 [N,1000] ImageNet logits."""
         n, _, hh, ww = x.shape
-        a0 = _empty((n * (hh // 4) * (ww // 4), 48), self.dt, self.dev)
-        L.stem_patchify_nchw(x, a0, n, hh, ww)
+        if FUSED_STEM and self.dt != torch.float32 and backend == L.GEMM_AUTO:
+            a0 = [(x, True, n, hh, ww)]
+        else:
+            a0 = _empty((n * (hh // 4) * (ww // 4), 48), self.dt, self.dev)
+            L.stem_patchify_nchw(x, a0, n, hh, ww)
         out = _empty((n, 1000), torch.float32, self.dev)
         self.forward_tokens(a0, [(n, hh // 4, ww // 4)], [(0, n, out, 1000)], act, backend)
         return out
@@ -342,9 +360,12 @@ class PackedED:
         dec, dh, dw = self.decode(e, n, h, w, backend)
         assert (dh, dw) == (hh, ww)
         th, tw = hh // 4, ww // 4
-        a0 = _empty((2 * n * th * tw, 48), dt, dev)
-        L.stem_patchify_nhwc(dec, a0, n, hh, ww)
-        L.stem_patchify_nchw(x, a0[n * th * tw:], n, hh, ww)
+        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO:
+            a0 = [(dec, False, n, hh, ww), (x, True, n, hh, ww)]
+        else:
+            a0 = _empty((2 * n * th * tw, 48), dt, dev)
+            L.stem_patchify_nhwc(dec, a0, n, hh, ww)
+            L.stem_patchify_nchw(x, a0[n * th * tw:], n, hh, ww)
         cat = _empty((n, 2000), dt, dev)
         self.backbone.forward_tokens(a0, [(2 * n, th, tw)], [(0, n, cat, 2000), (n, n, cat[:, 1000:], 2000)],
                                      L.ACT_GELU, backend)
@@ -445,9 +466,12 @@ class PackedVAE:
         t1 = (hh // 4, ww // 4)
         t2 = (h2 // 4, w2 // 4)
         m1 = n * t1[0] * t1[1]
-        a0 = _empty((m1 + n * t2[0] * t2[1], 48), dt, dev)
-        L.stem_patchify_nchw(x, a0, n, hh, ww)
-        L.stem_patchify_nhwc(xhat, a0[m1:], n, h2, w2)
+        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO:
+            a0 = [(x, True, n, hh, ww), (xhat, False, n, h2, w2)]
+        else:
+            a0 = _empty((m1 + n * t2[0] * t2[1], 48), dt, dev)
+            L.stem_patchify_nchw(x, a0, n, hh, ww)
+            L.stem_patchify_nhwc(xhat, a0[m1:], n, h2, w2)
         cat = _empty((n, 2000), dt, dev)
         self.backbone.forward_tokens(a0, [(n, *t1), (n, *t2)], [(0, n, cat, 2000), (n, n, cat[:, 1000:], 2000)],
                                      L.ACT_RELU, backend)

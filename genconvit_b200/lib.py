@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_stem_fused", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -74,6 +74,7 @@ def load():
     lib.gcv_conv3x3_first.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_im2col3x3.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_stem_fused.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
@@ -220,6 +221,15 @@ def ln_patchify2(x, a, ln_w, ln_b, eps, B, H, W, Cc):
     es = x.element_size()
     _run("ln_patchify2", 2.0 * B * H * W * Cc * es, lambda: load().gcv_ln_patchify2(
         DTYPE_CODE[x.dtype], _p(x), _p(a), _p(ln_w), _p(ln_b), eps, B, H, W, Cc, _stream()))
+
+
+def stem_fused(x, y, w, bias, ln_w, ln_b, eps, B, H, W, nchw):
+    """Conv2d(3,96,k4,s4) + bias + LayerNorm2d in one pass; see gcv_stem_fused."""
+    if nchw:
+        assert x.dtype == torch.float32
+    _run("stem_fused", B * H * W * 3.0 * x.element_size() + B * (H // 4) * (W // 4) * 96.0 * y.element_size(),
+         lambda: load().gcv_stem_fused(DTYPE_CODE[y.dtype], 1 if nchw else 0, _p(x), _p(y), _p(w), _p(bias), _p(ln_w),
+                                       _p(ln_b), eps, B, H, W, _stream()), f"B{B} H{H} {'nchw' if nchw else 'nhwc'}")
 
 
 def stem_patchify_nchw(x, a, B, H, W):

@@ -135,6 +135,12 @@ int gcv_dwconv7_stats(int dtype, const void* x, void* y, float* stats, const flo
                       int B, int H, int W, int C, void* stream);
 int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps,
                      int B, int H, int W, int C, void* stream);
+/* gcv_stem_fused (bf16/fp16): the whole ConvNeXt stem -- Conv2d(3,96,k4,s4) + bias + LayerNorm2d(96) (timm ConvNeXt.stem,
+ *   genconvit_ed.py:82-83 / genconvit_vae.py:111-112) -- in one pass on the tensor cores: frames in, NHWC tokens
+ *   y [B*(H/4)*(W/4), 96] out.  nchw != 0: x = fp32 [B,3,H,W] and w = [96][(c,kh,kw)] (the conv weight as stored);
+ *   nchw == 0: x = `dtype` [B,H,W,3] and w = [96][(kh,kw,c)] (the stem GEMM's B layout). */
+int gcv_stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
+                   const float* ln_b, float eps, int B, int H, int W, void* stream);
 int gcv_stem_patchify_nchw(int dtype, const float* x, void* a, int B, int H, int W, void* stream);
 int gcv_stem_patchify_nhwc(int dtype, const void* x, void* a, int B, int H, int W, void* stream);
 int gcv_layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps,

@@ -529,3 +529,28 @@ def test_conv3x3_c16_direct(shape, dtype):
     out = torch.full((B, H, W, 32), float("nan"), device=DEV, dtype=dtype)
     L.conv3x3_c16(x, out, wp, b, 1, L.ACT_RELU, False, B, H, W)
     _close(out, want, TOL[dtype], "conv3x3_c16 s1 relu")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 112, 112), (5, 32, 48)])
+def test_stem_fused(shape, dtype):
+    """Fused stem (Conv2d(3,96,4,4) + LayerNorm2d) vs torch conv2d + layer_norm in fp32 on the same 16-bit-rounded
+    operands, for both input layouts (fp32 NCHW frames, 16-bit NHWC reconstructions)."""
+    L = _lib()
+    B, H, W = shape
+    x = _rand(B, 3, H, W, seed=1)
+    w = _rand(96, 3, 4, 4, seed=2, scale=48 ** -0.5)
+    b, lw, lb = _rand(96, seed=3, scale=0.1), 1 + _rand(96, seed=4, scale=0.1), _rand(96, seed=5, scale=0.1)
+    wr = w.to(dtype).float()
+    M = B * (H // 4) * (W // 4)
+
+    def ref(xin):
+        t = F.conv2d(xin, wr, b, stride=4).permute(0, 2, 3, 1)
+        return F.layer_norm(t, (96,), lw, lb, 1e-6).reshape(M, 96)
+    out = torch.full((M, 96), float("nan"), device=DEV, dtype=dtype)
+    L.stem_fused(x, out, w.reshape(96, 48).to(dtype).contiguous(), b, lw, lb, 1e-6, B, H, W, True)
+    _close(out, ref(x.to(dtype).float()), TOL[dtype], "stem_fused nchw")
+    xh = x.permute(0, 2, 3, 1).contiguous().to(dtype)
+    out = torch.full((M, 96), float("nan"), device=DEV, dtype=dtype)
+    L.stem_fused(xh, out, w.permute(0, 2, 3, 1).reshape(96, 48).to(dtype).contiguous(), b, lw, lb, 1e-6, B, H, W, False)
+    _close(out, ref(xh.float().permute(0, 3, 1, 2)), TOL[dtype], "stem_fused nhwc")
