@@ -59,14 +59,15 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
   const int Wt = W >> 2, Ht = H >> 2;
   const int64_t tiles = (M + 15) >> 4;
   const int warps = (int)(gridDim.x * (ST_THREADS / 32));
-  for (int64_t tile = (int64_t)blockIdx.x * (ST_THREADS / 32) + (threadIdx.x >> 5); tile < tiles; tile += warps) {
-    // this lane's two tokens: rows g and g + 8 of the tile
-    uint32_t a[3][4];
+  // raw operands of a tile: loaded one tile ahead, so that their HBM latency overlaps the previous tile's MMAs,
+  // LayerNorm and stores (one CTA of 8 warps per SM: the loads in flight are what feeds the memory system)
+  using Raw = typename std::conditional<NCHW, float2, uint32_t>::type;
+  Raw raw[3][4];
+  auto load_raw = [&](int64_t tile) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       int64_t m = tile * 16 + g + 8 * r;
-      const bool ok = m < M;
-      if (!ok) m = M - 1;
+      if (m >= M) m = M - 1;
       const int ox = (int)(m % Wt);
       const int64_t q = m / Wt;
       const int oy = (int)(q % Ht);
@@ -76,10 +77,8 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
         const float* xb = reinterpret_cast<const float*>(xin) + ((b * 3) * H + 4 * oy + (t >> 1)) * (int64_t)W + 4 * ox + 2 * (t & 1);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const float2 lo = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W));
-          const float2 hi = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W + 2 * (int64_t)W));
-          a[s][r] = pack2<T>(lo.x, lo.y);
-          a[s][r + 2] = pack2<T>(hi.x, hi.y);
+          raw[s][r] = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W));
+          raw[s][r + 2] = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W + 2 * (int64_t)W));
         }
       } else {
         // k = kh*12 + kw*3 + c; patch row kh = 12 contiguous elements at pixel (4oy + kh, 4ox)
@@ -87,11 +86,25 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           const int k0 = 16 * s + 2 * t, k1 = k0 + 8;
-          a[s][r] = __ldg(reinterpret_cast<const uint32_t*>(xb + (int64_t)(k0 / 12) * W * 3 + k0 % 12));
-          a[s][r + 2] = __ldg(reinterpret_cast<const uint32_t*>(xb + (int64_t)(k1 / 12) * W * 3 + k1 % 12));
+          raw[s][r] = __ldg(reinterpret_cast<const uint32_t*>(xb + (int64_t)(k0 / 12) * W * 3 + k0 % 12));
+          raw[s][r + 2] = __ldg(reinterpret_cast<const uint32_t*>(xb + (int64_t)(k1 / 12) * W * 3 + k1 % 12));
         }
       }
     }
+  };
+  const int64_t tile_first = (int64_t)blockIdx.x * (ST_THREADS / 32) + (threadIdx.x >> 5);
+  if (tile_first < tiles) load_raw(tile_first);
+  for (int64_t tile = tile_first; tile < tiles; tile += warps) {
+    // this lane's two tokens: rows g and g + 8 of the tile
+    uint32_t a[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (NCHW) a[s][i] = pack2<T>(raw[s][i].x, raw[s][i].y);
+        else a[s][i] = raw[s][i];
+      }
+    if (tile + warps < tiles) load_raw(tile + warps);
     float acc[12][4];
 #pragma unroll
     for (int nt = 0; nt < 12; ++nt) {
