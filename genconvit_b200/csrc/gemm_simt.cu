@@ -61,6 +61,33 @@ gemm_simt_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, 
   }
 }
 
+// Skinny outputs (N <= 8, e.g. the 500 -> 2 classification head, genconvit_ed.py:75 / genconvit_vae.py:104): one warp
+// per output row, lanes stride over K (coalesced A reads, B rows from cache), fixed-order shuffle reduction.  The tiled
+// kernel above would run such a problem on 4 CTAs with 32 barrier-separated k-steps each.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, void* D, int64_t M, int N,
+                   int K, const gcv_epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  float acc[8] = {};
+  const T* a = A + m * lda;
+  for (int k = lane; k < K; k += 32) {
+    const float av = to_f<T>(a[k]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) acc[n] = fmaf(av, to_f<T>(B[(int64_t)n * ldb + k]), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (n < N) {
+      const float v = warp_sum(acc[n]);
+      if (lane == 0) epilogue_one<T>(ep, m, n, N, v, D, K);
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_simt(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M, int64_t N,
@@ -69,6 +96,27 @@ int gemm_simt(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
   const int64_t gm = (M + TM - 1) / TM, gn = (N + TN - 1) / TN;
   GCV_REQUIRE(gm <= 2147483647LL && gn <= 65535, "GEMM too large for the SIMT grid");
   dim3 g((unsigned)gm, (unsigned)gn);
+  if (N <= 8 && (M + 7) / 8 <= 2147483647LL) {
+    const unsigned gs = (unsigned)((M + 7) / 8);
+    switch (dtype) {
+      case GCV_F32:
+        gemm_skinny_kernel<float><<<gs, 256, 0, stream>>>(reinterpret_cast<const float*>(A), lda,
+                                                          reinterpret_cast<const float*>(B), ldb, D, M, (int)N, (int)K, *ep);
+        break;
+      case GCV_BF16:
+        gemm_skinny_kernel<__nv_bfloat16><<<gs, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(A), lda,
+                                                                  reinterpret_cast<const __nv_bfloat16*>(B), ldb, D, M,
+                                                                  (int)N, (int)K, *ep);
+        break;
+      case GCV_F16:
+        gemm_skinny_kernel<__half><<<gs, 256, 0, stream>>>(reinterpret_cast<const __half*>(A), lda,
+                                                           reinterpret_cast<const __half*>(B), ldb, D, M, (int)N, (int)K, *ep);
+        break;
+      default:
+        GCV_REQUIRE(false, "bad dtype %d", dtype);
+    }
+    return check_launch("gemm_simt");
+  }
   switch (dtype) {
     case GCV_F32:
       gemm_simt_kernel<float><<<g, 256, 0, stream>>>(reinterpret_cast<const float*>(A), lda,
