@@ -45,16 +45,23 @@ conv3x3_first_kernel(const float* __restrict__ x, T* __restrict__ y, const float
   constexpr int NP = POOL ? 2 : 1;          // conv outputs per dim feeding this thread's output
   constexpr int IN = (NP - 1) * STRIDE + 3; // input patch edge
   const int cy0 = ho * NP * STRIDE - 1, cx0 = wo * NP * STRIDE - 1;
+  // the three channel patches are loaded up front (48 independent loads in flight per thread), their addresses and
+  // bounds predicates computed once
   float patch[3][IN][IN];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
+  {
+    const float* xb = x + (b * 3) * (int64_t)H * W;
+    const int64_t plane = (int64_t)H * W;
 #pragma unroll
     for (int i = 0; i < IN; ++i)
 #pragma unroll
       for (int j = 0; j < IN; ++j) {
         const int yy = cy0 + i, xx = cx0 + j;
-        patch[c][i][j] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + ((b * 3 + c) * H + yy) * (int64_t)W + xx) : 0.0f;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const float* px = xb + (int64_t)yy * W + xx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) patch[c][i][j] = ok ? __ldg(px + c * plane) : 0.0f;
       }
+  }
   // all NP*NP conv positions advance together so each tap's 16 weights are read once
   // output channels in pairs: one FFMA2 (fma.rn.f32x2) per tap and channel pair -- the kernel is FMA-issue bound
   float2 acc[NP * NP][8];
