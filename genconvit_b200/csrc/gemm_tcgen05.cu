@@ -313,10 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int c = sub; c < chunks; c += 4) {
         const int n0 = n_blk * p.block_n + c * 32;
-        if (p.tma_store) {                               // the previous store of this warp must have drained the staging tile
-          if (elect_one()) tma_store_wait_read();
-          __syncwarp();
-        }
+
         // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 576-thread CTA
         // leaves 96 registers per thread)
 #pragma unroll
@@ -348,6 +345,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             continue;
           }
           // ---- phase A ----
+          if (h == 0 && p.tma_store) {                   // the previous bulk store of this warp must have drained the staging
+            if (elect_one()) tma_store_wait_read();      // tile: waited for as late as possible (after this chunk's TMEM load)
+            __syncwarp();
+          }
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const int j = h * 2 + jj;
