@@ -114,6 +114,7 @@ __device__ __forceinline__ __half2 gelu_fast_h2(__half2 x) {
 // Row statistics of the folded LayerNorm (gcv_epilogue.ln_stats): (rstd, -mean * rstd) of row m from its per-chunk
 // partial sums, so that LN-folded pre-activation = acc * rs + rm * colsum[n] + bias[n].
 __device__ __forceinline__ float2 ln_row_scale(const float* stats, int64_t m, int chunks, int K, float eps) {
+  if (chunks == 0) return __ldg(reinterpret_cast<const float2*>(stats) + m);   // already reduced by gcv_ln_finalize
   const float2* p = reinterpret_cast<const float2*>(stats) + m * chunks;
   float s = 0.0f, q = 0.0f;
   for (int i = 0; i < chunks; ++i) {

@@ -787,4 +787,38 @@ int pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, f
   });
 }
 
+
+// ---------------------------------------------------------------------------------
+// Reduce the LayerNorm partial sums written by dwconv7_stats ([M][chunks] x (sum, sumsq)) to one (rstd, -mean*rstd)
+// pair per row, once, instead of in every epilogue thread of the consuming GEMM (4 warps per row x every n-tile).
+// ---------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+ln_finalize_kernel(const float2* __restrict__ stats, float2* __restrict__ out, int64_t M, int chunks, int K, float eps) {
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m >= M) return;
+  if ((chunks & 1) == 0) {                       // 16-byte loads: two chunks at a time (rows are 8 * chunks bytes)
+    const float4* p = reinterpret_cast<const float4*>(stats + m * chunks);
+    float s = 0.0f, q = 0.0f;
+    for (int i = 0; i < chunks / 2; ++i) {
+      const float4 v = __ldg(p + i);
+      s += v.x; q += v.y;
+      s += v.z; q += v.w;
+    }
+    const float inv = 1.0f / (float)K, mean = s * inv;
+    const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, q * inv), 0.0f) + eps);
+    out[m] = make_float2(rstd, -mean * rstd);
+    return;
+  }
+  out[m] = ln_row_scale(reinterpret_cast<const float*>(stats), m, chunks, K, eps);
+}
+}  // namespace
+
+int ln_finalize(const float* stats, float* out, int64_t M, int chunks, int K, float eps, cudaStream_t stream) {
+  GCV_REQUIRE(M > 0 && chunks > 0 && K > 0, "ln_finalize: bad shape");
+  ln_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(stats),
+                                                                      reinterpret_cast<float2*>(out), M, chunks, K, eps);
+  return check_launch("ln_finalize");
+}
+
 }  // namespace gcv

@@ -645,7 +645,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
       ep->store == GCV_STORE_ROWS && N % 8 == 0)
     mode = 4;
   if (ep->ln_stats) {
-    GCV_REQUIRE(mode == 1 && ep->ln_colsum && ep->ln_chunks > 0 && N % 8 == 0,
+    GCV_REQUIRE(mode == 1 && ep->ln_colsum && ep->ln_chunks >= 0 && N % 8 == 0,
                 "tcgen05 GEMM: the folded LayerNorm needs bias + GELU, a 16-bit row-major output and N %% 8 == 0, N <= %d",
                 kVecMaxN);
     mode = 3;

@@ -136,6 +136,7 @@ class PackedConvNeXt:
             fold = LN_FOLD and backend == L.GEMM_AUTO and dt != torch.float32
             stats = _empty((m, c // 32, 2), torch.float32, dev) if fold else None
             hid = None if fused else _empty((m, 4 * c), dt, dev)
+            rowstat = _empty((m, 2), torch.float32, dev) if (fold and not fused) else None
             for blk in st["blocks"]:
                 r = 0
                 for b, h, w in segs:
@@ -151,7 +152,9 @@ class PackedConvNeXt:
                     L.mlp_fused(y, blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], blk["gamma"], x, m, c)
                 else:
                     if fold:
-                        L.gemm(y, blk["fc1_wf"], hid, m, 4 * c, c, bias=blk["fc1_bf"], act=L.ACT_GELU, ln_stats=stats,
+                        # partial sums -> one (rstd, -mean*rstd) pair per row, once, not in every epilogue thread
+                        L.ln_finalize(stats, rowstat, m, c, 1e-6)
+                        L.gemm(y, blk["fc1_wf"], hid, m, 4 * c, c, bias=blk["fc1_bf"], act=L.ACT_GELU, ln_stats=rowstat,
                                ln_colsum=blk["fc1_cs"], ln_eps=1e-6, backend=backend)
                     else:
                         L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)

@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_stem_fused", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -74,6 +74,7 @@ def load():
     lib.gcv_conv3x3_first.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_im2col3x3.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.gcv_ln_finalize.argtypes = [vp, vp, i64, i32, i32, f32, vp]
     lib.gcv_stem_fused.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -159,7 +160,8 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     ep.out_f32 = 1 if out_f32 else 0
     ep.ln_stats = ln_stats.data_ptr() if ln_stats is not None else None
     ep.ln_colsum = ln_colsum.data_ptr() if ln_colsum is not None else None
-    ep.ln_chunks = (K // 32) if ln_stats is not None else 0
+    # [M, chunks, 2] partial sums, or [M, 2] rows already reduced by ln_finalize (ln_chunks = 0)
+    ep.ln_chunks = (ln_stats.shape[1] if ln_stats.dim() == 3 else 0) if ln_stats is not None else 0
     ep.ln_eps = ln_eps
     lda_, ldb_ = (lda if lda is not None else K), (ldb if ldb is not None else K)
     tc = backend == GEMM_TCGEN05 or backend >= 1000 or (
@@ -221,6 +223,12 @@ def ln_patchify2(x, a, ln_w, ln_b, eps, B, H, W, Cc):
     es = x.element_size()
     _run("ln_patchify2", 2.0 * B * H * W * Cc * es, lambda: load().gcv_ln_patchify2(
         DTYPE_CODE[x.dtype], _p(x), _p(a), _p(ln_w), _p(ln_b), eps, B, H, W, Cc, _stream()))
+
+
+def ln_finalize(stats, out, M, K, eps):
+    """[M, chunks, 2] LayerNorm partial sums -> [M, 2] (rstd, -mean * rstd); see gcv_ln_finalize."""
+    _run("ln_finalize", M * (stats.shape[1] + 1) * 8.0, lambda: load().gcv_ln_finalize(
+        _p(stats), _p(out), M, stats.shape[1], K, eps, _stream()))
 
 
 def stem_fused(x, y, w, bias, ln_w, ln_b, eps, B, H, W, nchw):

@@ -133,6 +133,9 @@ int gcv_dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const f
  *   gcv_gemm (gcv_epilogue.ln_stats) / gcv_mlp_fused_ln.  stats may be NULL. */
 int gcv_dwconv7_stats(int dtype, const void* x, void* y, float* stats, const float* taps, const float* bias,
                       int B, int H, int W, int C, void* stream);
+/* gcv_ln_finalize: reduce gcv_dwconv7_stats' partial sums [M][chunks] x (sum, sumsq) to out [M] x (rstd, -mean*rstd)
+ *   (mean = sum/K, rstd = rsqrt(sumsq/K - mean^2 + eps)); pass `out` as gcv_epilogue.ln_stats with ln_chunks = 0. */
+int gcv_ln_finalize(const float* stats, float* out, int64_t M, int chunks, int K, float eps, void* stream);
 int gcv_ln_patchify2(int dtype, const void* x, void* a, const float* ln_w, const float* ln_b, float eps,
                      int B, int H, int W, int C, void* stream);
 /* gcv_stem_fused (bf16/fp16): the whole ConvNeXt stem -- Conv2d(3,96,k4,s4) + bias + LayerNorm2d(96) (timm ConvNeXt.stem,

@@ -274,6 +274,15 @@ def test_gemm_folded_layernorm(shape, dtype):
     L.gemm(v, w1f, d, M, N, K, bias=b1f, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6)
     torch.cuda.synchronize()
     _close(d, want, TOL[dtype], f"folded LN gemm {shape}")
+    # the same with the partial sums reduced once by ln_finalize ([M, 2] rows of (rstd, -mean * rstd), ln_chunks = 0)
+    rowstat = torch.full((M, 2), float("nan"), device=DEV)
+    L.ln_finalize(stats, rowstat, M, K, 1e-6)
+    mean, var = v.float().mean(1), v.float().var(1, unbiased=False)
+    _close(rowstat[:, 0], (var + 1e-6).rsqrt(), 1e-4, "ln_finalize rstd")
+    _close(rowstat[:, 1], -mean * (var + 1e-6).rsqrt(), 1e-4, "ln_finalize -mean*rstd")
+    d1 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
+    L.gemm(v, w1f, d1, M, N, K, bias=b1f, act=L.ACT_GELU, ln_stats=rowstat, ln_colsum=cs, ln_eps=1e-6)
+    _close(d1, want, TOL[dtype], f"folded LN gemm, finalised stats {shape}")
     # the SIMT back end implements the same epilogue
     if M <= 1000:
         d2 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)

@@ -32,3 +32,5 @@ timed("fc2 bias+gamma+res bn128", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b
 timed("fc2 bias+gamma+res bn256", lambda: L.gemm(hid, w2, x, M, C, 4 * C, bias=b2, gamma=g, residual=x, ldr=C, backend=1256), fl)
 timed("fc1 bias+gelu+ln bn192", lambda: L.gemm(a, w1, hid, M, 4 * C, C, bias=b1, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6, backend=1192), fl)
 timed("fc1 bias+gelu+ln bn128", lambda: L.gemm(a, w1, hid, M, 4 * C, C, bias=b1, act=L.ACT_GELU, ln_stats=stats, ln_colsum=cs, ln_eps=1e-6, backend=1128), fl)
+stats1 = torch.rand(M, 1, 2, device=dev)
+timed("fc1 bias+gelu+ln (1 stats chunk)", lambda: L.gemm(a, w1, hid, M, 4 * C, C, bias=b1, act=L.ACT_GELU, ln_stats=stats1, ln_colsum=cs, ln_eps=1e-6), fl)
