@@ -17,6 +17,8 @@ ap.add_argument("--dtype", default="bf16")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
+import model.genconvit as _gm  # noqa: E402
+_gm.set_two_streams(False)      # per-launch durations: no overlap between the two networks
 model = bench.build_model({"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype], dev)
 sc = VideoScorer(model, args.batch, 16, use_graph=False)
 sc.x_static.normal_().clamp_(-2.1, 2.6)
