@@ -140,7 +140,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (p.vec_smem) {
     // bias / layer-scale vectors are read by every epilogue thread for every tile: keep them on chip
     for (int i = threadIdx.x; i < p.N; i += kThreads) {
-      vec_bias[i] = p.ep.bias ? __ldg(p.ep.bias + i) : 0.0f;
+      // the GELU epilogues (MODE 1, 3) work on half the pre-activation: their staged bias is bias / 2
+      vec_bias[i] = p.ep.bias ? ((MODE == 1 || MODE == 3) ? 0.5f : 1.0f) * __ldg(p.ep.bias + i) : 0.0f;
       vec_gamma[i] = MODE == 3 ? __ldg(p.ep.ln_colsum + i) : (p.ep.gamma ? __ldg(p.ep.gamma + i) : 1.0f);
     }
   }
@@ -283,6 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float2 lnrs = make_float2(1.0f, 0.0f);             // folded LayerNorm: (rstd, -mean * rstd) of this thread's row,
       if constexpr (MODE == 3) {                         // fetched before blocking on the accumulator
         if (m < p.M && sub < chunks) lnrs = ln_row_scale(ep.ln_stats, m, ep.ln_chunks, p.K, ep.ln_eps);
+        lnrs.x *= 0.5f; lnrs.y *= 0.5f;                  // GELU is evaluated from x / 2 (ln_bias_gelu_pack8)
       }
       uint4 res[4];                                      // MODE 4: residual of this thread's row, 32 columns of a chunk
       auto fetch_residual = [&](int c) {

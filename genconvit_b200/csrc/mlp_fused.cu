@@ -149,7 +149,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < K::HC; i += kFThreads) {
-    vec_b1[i] = __ldg(p.b1 + i);
+    vec_b1[i] = 0.5f * __ldg(p.b1 + i);            // the GELU helpers work on half the pre-activation
     if constexpr (LN) vec_s1[i] = __ldg(p.colsum1 + i);
   }
   for (int i = threadIdx.x; i < C; i += kFThreads) {
@@ -437,6 +437,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             if (m < p.M) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
           }
           lnrs = ln_row_finish(ln_raw, C / 32, C, p.ln_eps);
+          lnrs.x *= 0.5f; lnrs.y *= 0.5f;
           ln_ti = ti;
           const int64_t mn = (int64_t)((int)blockIdx.x + (ti + 1) * (int)gridDim.x) * FM + row;
           if (mn < p.M) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
