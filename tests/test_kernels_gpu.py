@@ -541,7 +541,7 @@ def test_conv3x3_c16_direct(shape, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 112, 112), (5, 32, 48)])
+@pytest.mark.parametrize("shape", [(2, 224, 224), (3, 112, 112), (5, 32, 48), (3, 20, 28)])
 def test_stem_fused(shape, dtype):
     """Fused stem (Conv2d(3,96,4,4) + LayerNorm2d) vs torch conv2d + layer_norm in fp32 on the same 16-bit-rounded
     operands, for both input layouts (fp32 NCHW frames, 16-bit NHWC reconstructions)."""
