@@ -42,6 +42,8 @@ int conv3x3_first(int dtype, const float* x, void* y, const float* w, const floa
                   int B, int H, int W, cudaStream_t stream);
 int im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C, int stride, cudaStream_t stream);
 int maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, cudaStream_t stream);
+int conv3x3_c32(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool, int B,
+                int H, int W, cudaStream_t stream);
 int ln_finalize(const float* stats, float* out, int64_t M, int chunks, int K, float eps, cudaStream_t stream);
 int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
                const float* ln_b, float eps, int B, int H, int W, cudaStream_t stream);
@@ -176,6 +178,10 @@ int gcv_conv3x3_c16(int dtype, const void* x, void* y, const void* w, const floa
 int gcv_stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
                    const float* ln_b, float eps, int B, int H, int W, void* stream) {
   return stem_fused(dtype, nchw, x, y, w, bias, ln_w, ln_b, eps, B, H, W, S(stream));
+}
+int gcv_conv3x3_c32(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool,
+                    int B, int H, int W, void* stream) {
+  return conv3x3_c32(dtype, x, y, w, bias, stride, act, pool, B, H, W, S(stream));
 }
 int gcv_ln_finalize(const float* stats, float* out, int64_t M, int chunks, int K, float eps, void* stream) {
   return ln_finalize(stats, out, M, chunks, K, eps, S(stream));

@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -76,6 +76,7 @@ def load():
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_ln_finalize.argtypes = [vp, vp, i64, i32, i32, f32, vp]
     lib.gcv_stem_fused.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp]
+    lib.gcv_conv3x3_c32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
@@ -277,6 +278,14 @@ def conv3x3_c16(x, y, w, bias, stride, act, pool, B, H, W):
     """Direct 16 -> 32 channel 3x3 conv (+ act, + 2x2 max-pool) on the tensor cores; see gcv_conv3x3_c16."""
     es = x.element_size()
     _run("conv3x3_c16", (B * H * W * 16.0 + y.numel()) * es, lambda: load().gcv_conv3x3_c16(
+        DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), stride, act, 1 if pool else 0, B, H, W, _stream()),
+        f"B{B} H{H} W{W} s{stride}")
+
+
+def conv3x3_c32(x, y, w, bias, stride, act, pool, B, H, W):
+    """Direct 32 -> 64 channel 3x3 conv (+ act, + 2x2 max-pool) on the tensor cores; see gcv_conv3x3_c32."""
+    es = x.element_size()
+    _run("conv3x3_c32", (B * H * W * 32.0 + y.numel()) * es, lambda: load().gcv_conv3x3_c32(
         DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), stride, act, 1 if pool else 0, B, H, W, _stream()),
         f"B{B} H{H} W{W} s{stride}")
 

@@ -177,6 +177,10 @@ int gcv_im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C,
 int gcv_maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
 int gcv_conv3x3_c16(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act,
                     int pool, int B, int H, int W, void* stream);
+/* gcv_conv3x3_c32: the same for the third layer, Conv2d(32 -> 64, k3, pad 1): x [B,H,W,32], w [64][(kh,kw,ci)];
+ *   stride 1 + ReLU + 2x2 max-pool = genconvit_ed.py:22-24, stride 2 + LeakyReLU = genconvit_vae.py:22-24. */
+int gcv_conv3x3_c32(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act,
+                    int pool, int B, int H, int W, void* stream);
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act,
                        int B, int H, int W, int CI, int CO, void* stream);
 int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);

@@ -563,3 +563,32 @@ def test_stem_fused(shape, dtype):
     out = torch.full((M, 96), float("nan"), device=DEV, dtype=dtype)
     L.stem_fused(xh, out, w.permute(0, 2, 3, 1).reshape(96, 48).to(dtype).contiguous(), b, lw, lb, 1e-6, B, H, W, False)
     _close(out, ref(xh.float().permute(0, 3, 1, 2)), TOL[dtype], "stem_fused nhwc")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 20, 28), (1, 56, 56), (2, 18, 50)])
+def test_conv3x3_c32_direct(shape, dtype):
+    """Direct 32 -> 64 conv (weights in shared memory, ldmatrix operands) vs torch conv2d (fp32) on the same rounded
+    inputs: stride 1 + ReLU + 2x2 max-pool (genconvit_ed.py:22-24), stride 2 + LeakyReLU (genconvit_vae.py:22-24)."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_conv3x3
+    B, H, W = shape
+    x = _rand(B, H, W, 32, dtype=dtype, seed=1)
+    w = _rand(64, 32, 3, 3, seed=2, scale=288 ** -0.5)
+    b = _rand(64, seed=3, scale=0.1)
+    wp = _pack_conv3x3(w, DEV, dtype)
+    wr = wp.float().reshape(64, 3, 3, 32).permute(0, 3, 1, 2)
+    xin = x.float().permute(0, 3, 1, 2)
+    want = F.max_pool2d(F.relu(F.conv2d(xin, wr, b, padding=1)), 2).permute(0, 2, 3, 1)
+    out = torch.full((B, H // 2, W // 2, 64), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c32(x, out, wp, b, 1, L.ACT_RELU, True, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c32 s1 relu pool")
+    want = F.leaky_relu(F.conv2d(xin, wr, b, stride=2, padding=1), 0.01).permute(0, 2, 3, 1)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, Ho, Wo, 64), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c32(x, out, wp, b, 2, L.ACT_LEAKY, False, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c32 s2 leaky")
+    want = F.relu(F.conv2d(xin, wr, b, padding=1)).permute(0, 2, 3, 1)
+    out = torch.full((B, H, W, 64), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_c32(x, out, wp, b, 1, L.ACT_RELU, False, B, H, W)
+    _close(out, want, TOL[dtype], "conv3x3_c32 s1 relu")
