@@ -24,7 +24,7 @@ int dispatch(int dtype, F&& f) {
 // from shared memory.  Output NHWC, 16 channels = two 16-byte stores (16-bit T).
 // ---------------------------------------------------------------------------------
 template <typename T, int STRIDE, bool POOL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, POOL ? 4 : 8)
 conv3x3_first_kernel(const float* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
                      const float* __restrict__ bias, int act, int B, int H, int W, int Ho, int Wo) {
   __shared__ __align__(16) float ws[27][16];   // [ci*9 + kh*3 + kw][co]
