@@ -1,6 +1,8 @@
 // Autoencoder / VAE side kernels and the scoring kernel.
 //   reference model/genconvit_ed.py:13-33 (Encoder), model/genconvit_vae.py:15-31 (Encoder.features),
 //   model/genconvit_vae.py:105,116 (Resize of the returned x_hat), model/pred_func.py:111-131 (scoring).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gcv {
@@ -280,6 +282,155 @@ score_videos_kernel(const float* __restrict__ logits, int n_nets, int n_frames, 
   }
 }
 
+
+// ---- first 3x3 conv on the tensor cores (16-bit modes) -----------------------------------------------------------
+// The FFMA kernel above needs 432 FMAs per conv pixel and is issue-bound at ~1 TB/s.  Here the frame tile is staged
+// once in shared memory as 16-bit RGB0 pixels (8 B each, zero outside the image = the conv padding) and the conv runs
+// as mma.sync m16n8k16 with K = (tap, channel) = 9 x 4 = 36 padded to 48 (three slices), N = 16 (two n-tiles): lane
+// (g, t) needs for K index 16s + 8h + 2t the channel pair 2(t%2) of tap 4s + 2h + t/2 -- one 32-bit shared-memory load.
+// A warp owns two conv rows of the tile (the two rows of a pooled row) and walks 7 segments of 16 pixels.
+constexpr int C1_ROWS = 16, C1_SEGS = 7, C1_COLS = 16 * C1_SEGS;      // conv-output tile: 16 rows x 112 columns
+
+template <typename T>
+__device__ __forceinline__ void c1_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (std::is_same<T, __half>::value)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T, int STRIDE, bool POOL>
+__global__ void __launch_bounds__(256)
+conv3x3_first_mma_kernel(const float* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
+                         const float* __restrict__ bias, int act, int B, int H, int W, int Hc, int Wc, int tiles_x,
+                         int tiles_y, int n_tiles) {
+  constexpr int IN_H = C1_ROWS * STRIDE + 2, IN_W = C1_COLS * STRIDE + 2;
+  extern __shared__ __align__(16) uint8_t c1sm[];
+  uint2* tile = reinterpret_cast<uint2*>(c1sm);                       // [IN_H][IN_W] pixels of 4 x 16 bit (R, G, B, 0)
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(c1sm);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // B fragments and this lane's tap offsets: K index k = 16s + 8h + 2t (+1): tap = k / 4, channel = k % 4
+  uint32_t bf[3][2][2], aoff[3][2];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 16 * s + 8 * h + 2 * t, tap = k >> 2, c = k & 3;      // c = 0 or 2
+      const bool ok = tap < 9;
+      const int kh = ok ? tap / 3 : 0, kw = ok ? tap % 3 : 0;
+      aoff[s][h] = (uint32_t)((kh * IN_W + kw) * 8 + c * 2);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int co = nt * 8 + g;
+        const float w0 = ok ? __ldg(w + co * 27 + c * 9 + tap) : 0.0f;                       // OIHW: [co][c][kh][kw]
+        const float w1 = (ok && c + 1 < 3) ? __ldg(w + co * 27 + (c + 1) * 9 + tap) : 0.0f;   // channel 3 is the zero pad
+        bf[s][nt][h] = pack2<T>(w0, w1);
+      }
+    }
+  float bv[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    bv[nt][0] = __ldg(bias + nt * 8 + 2 * t);
+    bv[nt][1] = __ldg(bias + nt * 8 + 2 * t + 1);
+  }
+  const int Ho = POOL ? Hc / 2 : Hc, Wo = POOL ? Wc / 2 : Wc;
+  for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const int b = tl / (tiles_x * tiles_y), r = tl - b * (tiles_x * tiles_y);
+    const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    const int iy0 = ty * C1_ROWS * STRIDE - 1, ix0 = tx * C1_COLS * STRIDE - 1;
+    const float* xb = x + (int64_t)b * 3 * H * W;
+    __syncthreads();                                   // the previous tile's readers are done
+    // four pixels per thread and pass: all twelve loads are issued before the first one is consumed
+    for (int i0 = threadIdx.x; i0 < IN_H * IN_W; i0 += 4 * 256) {
+      float c[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        const int py = i / IN_W, px = i - py * IN_W;
+        const int iy = iy0 + py, ix = ix0 + px;
+        const bool ok = i < IN_H * IN_W && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const float* p = xb + (int64_t)iy * W + ix;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) c[u][ch] = ok ? __ldg(p + ch * (int64_t)H * W) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < IN_H * IN_W) tile[i] = make_uint2(pack2<T>(c[u][0], c[u][1]), pack2<T>(c[u][2], 0.0f));
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int seg = 0; seg < C1_SEGS; ++seg) {
+      float acc[2][2][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          acc[rr][nt][0] = acc[rr][nt][2] = bv[nt][0];
+          acc[rr][nt][1] = acc[rr][nt][3] = bv[nt][1];
+        }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        // pixel (row 2*warp + rr, column seg*16 + g [+ 8]) of the conv tile -> top-left input pixel of its 3x3 window
+        const uint32_t base = tile_s + (uint32_t)((((2 * warp + rr) * STRIDE) * IN_W + (seg * 16 + g) * STRIDE) * 8);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          uint32_t a[4];
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[0]) : "r"(base + aoff[s][0]));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[1]) : "r"(base + aoff[s][0] + 8 * STRIDE * 8));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[2]) : "r"(base + aoff[s][1]));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[3]) : "r"(base + aoff[s][1] + 8 * STRIDE * 8));
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) c1_mma<T>(acc[rr][nt], a, bf[s][nt][0], bf[s][nt][1]);
+        }
+      }
+      // acc[rr][nt][e]: conv row ty*16 + 2*warp + rr, column tx*112 + seg*16 + g (e < 2) / + 8 (e >= 2), channel nt*8 + 2t + (e & 1)
+      if constexpr (POOL) {
+        const int py = ty * (C1_ROWS / 2) + warp;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          float m[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float vmax = fmaxf(acc[0][nt][e], acc[1][nt][e]);
+            m[e] = apply_act(fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4)), act);      // monotone act: after the max
+          }
+          if (((g & 1) == 0) == (nt == 0) && py < Ho) {          // even-g lanes store n-tile 0, odd-g lanes n-tile 1
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int px = tx * (C1_COLS / 2) + seg * 8 + (g >> 1) + 4 * hh;
+              if (px < Wo)
+                *reinterpret_cast<uint32_t*>(y + (((int64_t)b * Ho + py) * Wo + px) * 16 + nt * 8 + 2 * t) =
+                    pack2<T>(m[2 * hh], m[2 * hh + 1]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int oy = ty * C1_ROWS + 2 * warp + rr;
+          if (oy < Ho) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ox = tx * C1_COLS + seg * 16 + g + 8 * hh;
+              if (ox < Wo) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+                  *reinterpret_cast<uint32_t*>(y + (((int64_t)b * Ho + oy) * Wo + ox) * 16 + nt * 8 + 2 * t) =
+                      pack2<T>(apply_act(acc[rr][nt][2 * hh], act), apply_act(acc[rr][nt][2 * hh + 1], act));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
 }  // namespace
 
 int conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b, int stride, int act, int pool,
@@ -290,6 +441,38 @@ int conv3x3_first(int dtype, const float* x, void* y, const float* w, const floa
   const int Ho = pool ? Hc / 2 : Hc, Wo = pool ? Wc / 2 : Wc;
   const int64_t total = (int64_t)B * Ho * Wo;
   const unsigned grid = (unsigned)((total + 127) / 128);
+  static int mma_env = -1;                      // GCV_CONV1_MMA=0 keeps the fp32 FFMA kernel in the 16-bit modes (A/B timing)
+  if (mma_env < 0) { const char* e = getenv("GCV_CONV1_MMA"); mma_env = e ? atoi(e) : 1; }
+  if (mma_env && (dtype == GCV_BF16 || dtype == GCV_F16) && (!pool || (Hc % 2 == 0 && Wc % 2 == 0))) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles_x = (Wc + C1_COLS - 1) / C1_COLS, tiles_y = (Hc + C1_ROWS - 1) / C1_ROWS;
+    const int64_t n_tiles64 = (int64_t)B * tiles_x * tiles_y;
+    GCV_REQUIRE(n_tiles64 < 2147483647LL, "conv3x3_first: too many tiles");
+    const int n_tiles = (int)n_tiles64;
+    const size_t smem = (size_t)(C1_ROWS * stride + 2) * (C1_COLS * stride + 2) * 8;
+    const int per_sm = stride == 1 ? 4 : 2;
+    const unsigned g2 = (unsigned)(n_tiles < per_sm * sms ? n_tiles : per_sm * sms);
+    return dispatch(dtype, [&](auto tag) -> int {
+      using T = decltype(tag);
+      if constexpr (std::is_same<T, float>::value) {
+        return GCV_ERR_BAD_ARG;
+      } else {
+        auto go = [&](auto kernel) {
+          cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          kernel<<<g2, 256, smem, stream>>>(x, reinterpret_cast<T*>(y), w, b, act, B, H, W, Hc, Wc, tiles_x, tiles_y, n_tiles);
+        };
+        if (stride == 1 && pool) go(conv3x3_first_mma_kernel<T, 1, true>);
+        else if (stride == 1) go(conv3x3_first_mma_kernel<T, 1, false>);
+        else go(conv3x3_first_mma_kernel<T, 2, false>);
+        return check_launch("conv3x3_first");
+      }
+    });
+  }
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     if (stride == 1 && pool)
