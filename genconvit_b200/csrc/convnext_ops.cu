@@ -461,6 +461,71 @@ layernorm_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const float* _
   group_ln_row<T, LPR, ITER>(x + row * C, y + row * C, w, b, eps, C, threadIdx.x % LPR);
 }
 
+// Two rows per lane group (same weights): both rows' loads are in flight together and the index arithmetic is shared.
+template <typename T, int LPR, int ITER>
+__device__ __forceinline__ void group_ln_row2(const T* __restrict__ src0, const T* __restrict__ src1, T* __restrict__ dst0,
+                                              T* __restrict__ dst1, const float* __restrict__ w,
+                                              const float* __restrict__ b, float eps, int C, int gl) {
+  float v0[ITER][8], v1[ITER][8];
+  float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+      load8<T>(src0 + c, v0[i]);
+      load8<T>(src1 + c, v1[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s0 += v0[i][e]; s1 += v1[i][e]; }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const float mean0 = s0 / (float)C, mean1 = s1 / (float)C;
+  float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q0 += (v0[i][e] - mean0) * (v0[i][e] - mean0);
+        q1 += (v1[i][e] - mean1) * (v1[i][e] - mean1);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+  }
+  const float r0 = rsqrtf(q0 / (float)C + eps), r1 = rsqrtf(q1 / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int c = (gl + i * LPR) * 8;
+    if (c < C) {
+      float g[8], be[8];
+      load8<float>(w + c, g);
+      load8<float>(b + c, be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v0[i][e] = (v0[i][e] - mean0) * r0 * g[e] + be[e];
+        v1[i][e] = (v1[i][e] - mean1) * r1 * g[e] + be[e];
+      }
+      store8<T>(dst0 + c, v0[i]);
+      store8<T>(dst1 + c, v1[i]);
+    }
+  }
+}
+
 // LayerNorm2d over C of every pixel, written straight into the im2col matrix of the
 // following 2x2 stride-2 conv: pixel (2ho+kh, 2wo+kw) -> row (b,ho,wo), columns
 // [(kh*2+kw)*C, +C).  Pixels of an odd last row/column are dropped (floor semantics).
@@ -468,19 +533,20 @@ template <typename T, int LPR, int ITER>
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const T* __restrict__ x, T* __restrict__ a, const float* __restrict__ w,
                     const float* __restrict__ b, float eps, int B, int H, int W, int C) {
+  // one lane group per horizontal pixel pair (2wo, 2wo+1) of an input row: 2C contiguous elements in, 2C out
   constexpr int RPB = 256 / LPR;
   const int Ho = H / 2, Wo = W / 2;
   int64_t idx = (int64_t)blockIdx.x * RPB + threadIdx.x / LPR;
-  const int64_t total = (int64_t)B * Ho * 2 * Wo * 2;
+  const int64_t total = (int64_t)B * Ho * 2 * Wo;
   if (idx >= total) idx = total - 1;
-  const int wi = (int)(idx % (2 * Wo));
-  const int64_t t = idx / (2 * Wo);
+  const int wo = (int)(idx % Wo);
+  const int64_t t = idx / Wo;
   const int hi = (int)(t % (2 * Ho));
   const int64_t bi = t / (2 * Ho);
-  const T* src = x + ((bi * H + hi) * W + wi) * C;
-  const int64_t row = (bi * Ho + (hi >> 1)) * Wo + (wi >> 1);
-  T* dst = a + row * (4 * (int64_t)C) + ((hi & 1) * 2 + (wi & 1)) * C;
-  group_ln_row<T, LPR, ITER>(src, dst, w, b, eps, C, threadIdx.x % LPR);
+  const T* src = x + ((bi * H + hi) * W + 2 * wo) * C;
+  const int64_t row = (bi * Ho + (hi >> 1)) * Wo + wo;
+  T* dst = a + row * (4 * (int64_t)C) + (hi & 1) * 2 * C;
+  group_ln_row2<T, LPR, ITER>(src, src + C, dst, dst + C, w, b, eps, C, threadIdx.x % LPR);
 }
 
 // pick (lanes per row, vectors per lane) for a channel count; C % 8 == 0, C <= 2048
@@ -737,7 +803,7 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
 int ln_patchify2(int dtype, const void* x, void* a, const float* w, const float* b, float eps, int B, int H, int W, int C,
                  cudaStream_t stream) {
   GCV_REQUIRE(C % 8 == 0 && C <= 2048 && H >= 2 && W >= 2, "ln_patchify2: unsupported C=%d H=%d W=%d", C, H, W);
-  const int64_t total = (int64_t)B * (H / 2) * 2 * (W / 2) * 2;
+  const int64_t total = (int64_t)B * (H / 2) * 2 * (W / 2);          // horizontal pixel pairs
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     return ln_dispatch(C, [&](auto lpr, auto iter) -> int {
