@@ -24,6 +24,25 @@ int check_launch(const char* what) {
   return GCV_OK;
 }
 
+int device_sms() {
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev & 63;
+  if (!sms[slot]) cudaDeviceGetAttribute(&sms[slot], cudaDevAttrMultiProcessorCount, dev);
+  return sms[slot];
+}
+
+bool first_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64) return true;                       // beyond the latch: redo the (idempotent) setup every time
+  const unsigned long long bit = 1ull << dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 bool tcgen05_eligible(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t K);
 int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t M, int64_t N,
                  int64_t K, const gcv_epilogue* ep, int force_block_n, cudaStream_t stream);

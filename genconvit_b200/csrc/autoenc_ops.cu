@@ -444,12 +444,7 @@ int conv3x3_first(int dtype, const float* x, void* y, const float* w, const floa
   static int mma_env = -1;                      // GCV_CONV1_MMA=0 keeps the fp32 FFMA kernel in the 16-bit modes (A/B timing)
   if (mma_env < 0) { const char* e = getenv("GCV_CONV1_MMA"); mma_env = e ? atoi(e) : 1; }
   if (mma_env && (dtype == GCV_BF16 || dtype == GCV_F16) && (!pool || (Hc % 2 == 0 && Wc % 2 == 0))) {
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     const int tiles_x = (Wc + C1_COLS - 1) / C1_COLS, tiles_y = (Hc + C1_ROWS - 1) / C1_ROWS;
     const int64_t n_tiles64 = (int64_t)B * tiles_x * tiles_y;
     GCV_REQUIRE(n_tiles64 < 2147483647LL, "conv3x3_first: too many tiles");

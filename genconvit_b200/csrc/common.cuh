@@ -14,6 +14,10 @@ namespace gcv {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+// Per-DEVICE host state (a process may drive several GPUs): the SM count of the current device, and a one-time-setup
+// latch per (flag word, current device) for things like cudaFuncSetAttribute, which only applies to one device.
+int device_sms();
+bool first_on_device(unsigned long long& mask);
 
 #define GCV_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -156,6 +160,14 @@ __device__ __forceinline__ __half2 gelu_from_half_h2(__half2 h) {
   return __hfma2(h, t, h);
 }
 
+// fp32 pair -> packed fp16 with SATURATION to +-65504 (one F2FP.SATFINITE): an overflowing pre-activation must not become
+// -inf, for which gelu_from_half_h2 would evaluate (-inf) * (-1) + (-inf) = NaN instead of 0
+__device__ __forceinline__ __half2 f2h2_sat(const float2 v) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+  return *reinterpret_cast<__half2*>(&r);
+}
+
 // x0..x3 hold HALF the pre-activations
 template <typename T>
 __device__ __forceinline__ uint4 gelu_pack8_h2(const __half2 x0, const __half2 x1, const __half2 x2, const __half2 x3) {
@@ -192,8 +204,7 @@ __device__ __forceinline__ uint4 ln_bias_gelu_pack8(const float* w, const float 
   const float2 x1 = fma2(make_float2(w[2], w[3]), rs2, fma2(rm2, make_float2(s0.z, s0.w), make_float2(b0.z, b0.w)));
   const float2 x2 = fma2(make_float2(w[4], w[5]), rs2, fma2(rm2, make_float2(s1.x, s1.y), make_float2(b1.x, b1.y)));
   const float2 x3 = fma2(make_float2(w[6], w[7]), rs2, fma2(rm2, make_float2(s1.z, s1.w), make_float2(b1.z, b1.w)));
-  return gelu_pack8_h2<T>(__floats2half2_rn(x0.x, x0.y), __floats2half2_rn(x1.x, x1.y), __floats2half2_rn(x2.x, x2.y),
-                          __floats2half2_rn(x3.x, x3.y));
+  return gelu_pack8_h2<T>(f2h2_sat(x0), f2h2_sat(x1), f2h2_sat(x2), f2h2_sat(x3));
 }
 
 // bias + GELU on 8 fp32 accumulators -> 8 packed 16-bit outputs (T = __half or __nv_bfloat16).  The caller passes
@@ -205,8 +216,7 @@ __device__ __forceinline__ uint4 bias_gelu_pack8(const float* w, const float4 b0
   const float2 x1 = fma2(make_float2(w[2], w[3]), hf, make_float2(b0.z, b0.w));
   const float2 x2 = fma2(make_float2(w[4], w[5]), hf, make_float2(b1.x, b1.y));
   const float2 x3 = fma2(make_float2(w[6], w[7]), hf, make_float2(b1.z, b1.w));
-  return gelu_pack8_h2<T>(__floats2half2_rn(x0.x, x0.y), __floats2half2_rn(x1.x, x1.y), __floats2half2_rn(x2.x, x2.y),
-                          __floats2half2_rn(x3.x, x3.y));
+  return gelu_pack8_h2<T>(f2h2_sat(x0), f2h2_sat(x1), f2h2_sat(x2), f2h2_sat(x3));
 }
 
 __device__ __forceinline__ float apply_act_fast(float v, int act) {

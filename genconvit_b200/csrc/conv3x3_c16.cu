@@ -200,20 +200,14 @@ int conv3x3_c16(int dtype, const void* x, void* y, const void* w, const float* b
   const int64_t n_tiles64 = (int64_t)B * tiles_x * tiles_y;
   GCV_REQUIRE(n_tiles64 < 2147483647LL, "conv3x3_c16: too many tiles");
   const int n_tiles = (int)n_tiles64;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sms();
   const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
 #define GCV_CONV_LAUNCH(T, S, P)                                                                                         \
   do {                                                                                                                   \
     const size_t smem = 2 * (size_t)CGeom<S>::BYTES;                                                                     \
-    static bool attr_done = false;                                                                                       \
-    if (!attr_done) {                                                                                                    \
+    static unsigned long long attr_devs = 0;                                                                                       \
+    if (first_on_device(attr_devs)) {                                                                                                    \
       cudaFuncSetAttribute(conv3x3_c16_kernel<T, S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-      attr_done = true;                                                                                                  \
     }                                                                                                                    \
     conv3x3_c16_kernel<T, S, P><<<grid, CTHREADS, smem, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), \
                                                                   reinterpret_cast<const T*>(w), bias, act, B, H, W, Ho,  \

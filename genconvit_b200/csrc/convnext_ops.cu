@@ -732,12 +732,7 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
     int depth = (int)((224 * 1024 - fixed) / step_bytes);
     if (depth > 8) depth = 8;
     const size_t smem = fixed + depth * step_bytes;
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     const int grid = (int)(n_strips < sms ? n_strips : sms);
     // 4-D view [B][H][W][C] of the NHWC activation; box = (channel box, 13 pixels, 1 row, 1 image)
     CUtensorMap tm;
@@ -765,10 +760,9 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
       using T = decltype(tag);
       auto launch = [&](auto cc) -> int {
         constexpr int CC = decltype(cc)::value;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static unsigned long long attr_devs = 0;
+        if (first_on_device(attr_devs)) {
           cudaFuncSetAttribute(dwconv7_ln_col_kernel<T, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-          attr_done = true;
         }
         dwconv7_ln_col_kernel<T, CC><<<grid, threads, smem, stream>>>(
             tm, reinterpret_cast<T*>(y), taps, bias, ln_w, ln_b, eps, H, W, strips_w, (int)n_strips, depth);
@@ -788,10 +782,9 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     const size_t smem = DW_HH * DW_HW * DW_CK * sizeof(T) + (size_t)DW_TH * DW_TW * C * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_devs = 0;
+    if (first_on_device(attr_devs)) {
       cudaFuncSetAttribute(dwconv7_ln_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = true;
     }
     GCV_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C=%d needs %zu B of shared memory", C, smem);
     dwconv7_ln_kernel<T><<<(unsigned)grid, 128, smem, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y),

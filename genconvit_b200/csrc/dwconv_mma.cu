@@ -309,12 +309,7 @@ int dwconv7_mma(int dtype, const void* x, void* y, float* stats, const float* ta
   GCV_REQUIRE(n_tiles64 * H < 2147483647LL, "dwconv7_mma: too many pipeline steps");
   GCV_REQUIRE(((int64_t)igroups * MM_IMGS + 1) * H * W * C * 2 < 4294967295LL, "dwconv7_mma: tensor larger than 4 GiB");
   const int n_tiles = (int)n_tiles64;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sms();
   GCV_REQUIRE(n_chunks <= sms, "dwconv7_mma: C=%d has more channel chunks than the device has SMs", C);
   const int tile_slots = sms / n_chunks;                    // tiles in flight; every one gets all its channel chunks
   const int grid = (n_tiles < tile_slots ? n_tiles : tile_slots) * n_chunks;
@@ -340,10 +335,9 @@ int dwconv7_mma(int dtype, const void* x, void* y, float* stats, const float* ta
   }
   auto launch = [&](auto tag) -> int {
     using T = decltype(tag);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_devs = 0;
+    if (first_on_device(attr_devs)) {
       cudaFuncSetAttribute(dwconv7_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      attr_done = true;
     }
     dwconv7_mma_kernel<T><<<grid, MM_THREADS, smem, stream>>>(tm, reinterpret_cast<T*>(y), reinterpret_cast<float2*>(stats), taps, bias, B, H, W, C, xtiles,
                                                              n_tiles, n_chunks);

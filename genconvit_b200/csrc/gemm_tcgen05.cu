@@ -564,12 +564,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
               "tcgen05 GEMM needs bf16/fp16, 16-byte aligned A/B and K, lda, ldb multiples of 8 (K=%lld lda=%lld ldb=%lld)",
               (long long)K, (long long)lda, (long long)ldb);
   GCV_REQUIRE(M > 0 && N > 0 && N < (1 << 30), "bad GEMM shape");
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sms();
   Params p{};
   p.M = M; p.N = (int)N; p.K = (int)K;
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, (int)N, sms);
@@ -676,13 +671,12 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
     mode = 3;
   }
   cudaError_t le = cudaSuccess;
-  static bool attr_set[2][5][2] = {};
-  bool& attr_done = attr_set[dtype == GCV_BF16 ? 0 : 1][mode][duo ? 1 : 0];
+  static unsigned long long attr_set[2][5][2] = {};         // per kernel instantiation: devices whose smem limit is raised
+  unsigned long long& attr_devs = attr_set[dtype == GCV_BF16 ? 0 : 1][mode][duo ? 1 : 0];
   auto launch = [&](auto kernel) {
-    if (!attr_done) {
+    if (first_on_device(attr_devs)) {
       le = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
       if (le != cudaSuccess) return;
-      attr_done = true;
     }
     if (!duo) {
       kernel<<<grid, kThreads, kDynSmem, stream>>>(ma, mb, md, D, p);

@@ -564,21 +564,15 @@ int launch_fused_impl(int dtype, const void* y, const void* w1, const void* w2, 
   if (rc) return rc;
   if ((rc = fused_map(&m1, dtype, w1, K::HC, C, FCH))) return rc;
   if ((rc = fused_map(&m2, dtype, w2, C, K::HC, C))) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devs = 0;
+  if (first_on_device(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<T, C, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(fused MLP smem=%d): %s", K::SMEM, cudaGetErrorString(e));
       return GCV_ERR_CUDA;
     }
-    attr = true;
   }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sms();
   const int grid = p.tiles < sms ? p.tiles : sms;
   mlp_fused_kernel<T, C, LN><<<grid, kFThreads, K::SMEM, stream>>>(my, m1, m2, p);
   return check_launch("mlp_fused");

@@ -177,12 +177,7 @@ int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const
                   (reinterpret_cast<uintptr_t>(w) & 3) == 0,
               "stem_fused: misaligned pointer");
   const int64_t M = (int64_t)B * (H / 4) * (W / 4);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sms();
   const int64_t tiles = (M + 15) / 16, per_cta = ST_THREADS / 32;
   const int64_t want = (tiles + per_cta - 1) / per_cta;
   const int grid = (int)(want < sms ? want : sms);   // ~200 registers per thread: one CTA per SM

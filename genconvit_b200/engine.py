@@ -31,6 +31,19 @@ LN_FOLD = os.environ.get("GCV_NO_LNFOLD", "0") != "1"
 FUSED_STEM = os.environ.get("GCV_NO_FUSED_STEM", "0") != "1"
 
 
+def _on_device(fn):
+    """Run a forward with the tensor's device as the current CUDA device: the C ABI launches on the current device's
+    stream and keeps per-device kernel attributes, so a model on cuda:1 must not launch from cuda:0's context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, x, *a, **k):
+        L.require_cuda_tensor(x, type(self).__name__)
+        with torch.cuda.device(x.device):
+            return fn(self, x, *a, **k)
+    return wrapped
+
+
 def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
@@ -172,6 +185,7 @@ class PackedConvNeXt:
             L.gemm(pooled[first:], self.head_w, view, cnt, 1000, c, bias=self.head_b, act=act, ldd=ldd,
                    out_f32=view.dtype == torch.float32 and dt != torch.float32, backend=backend)
 
+    @_on_device
     def forward_images(self, x, act=L.ACT_NONE, backend=L.GEMM_AUTO):
         """``backbone(x)`` for fp32 NCHW frames -> fp32 [N,1000] ImageNet logits."""
         n, _, hh, ww = x.shape
@@ -224,6 +238,7 @@ class PackedSwin:
         self.norm = (_f32(sd["norm.weight"], dev), _f32(sd["norm.bias"], dev))
         self.head_w, self.head_b = _cd(sd["head.weight"], dev, dt), _f32(sd["head.bias"], dev)
 
+    @_on_device
     def forward_images(self, x, backend=L.GEMM_AUTO):
         """fp32 NCHW 224x224 frames -> fp32 [N,1000] logits (timm SwinTransformer.forward)."""
         dev, dt = self.dev, self.dt
@@ -356,6 +371,7 @@ class PackedED:
         """Decoder (genconvit_ed.py:43-61): -> NHWC [N, 32h, 32w, 3]."""
         return _run_convt_stack(e, self.dec, n, h, w, L.ACT_RELU, self.dt, self.dev, backend)
 
+    @_on_device
     def forward(self, x, backend=L.GEMM_AUTO):
         """GenConViTED.forward (genconvit_ed.py:77-89) -> fp32 logits [N,2].
 
@@ -364,6 +380,9 @@ class PackedED:
         """
         dev, dt = self.dev, self.dt
         n, _, hh, ww = x.shape
+        if x.shape[1] != 3 or hh % 32 or ww % 32 or hh < 32 or ww < 32:
+            # five 2x2 max-pools, then five k2s2 transposed convs must give back H x W (genconvit_ed.py:13-61,81-83)
+            raise ValueError(f"GenConViTED takes [N,3,H,W] frames with H, W multiples of 32, got {tuple(x.shape)}")
         e, h, w = self.encode(x, backend)
         dec, dh, dw = self.decode(e, n, h, w, backend)
         assert (dh, dw) == (hh, ww)
@@ -448,6 +467,8 @@ class PackedVAE:
         z = eps * exp(0.5*mu) + mu  (genconvit_vae.py:43-49; std comes from ``mu``, evaluated once).
         ``eps`` is [N,12544] fp32 in the reference's latent order; z is NHWC [N*49, 256]."""
         n = feat.shape[0]
+        if feat.shape[1] != 25088:
+            raise ValueError(f"VAE latent layer takes 25088 features per frame, got {feat.shape[1]}")
         z = _empty((n * 49, 256), self.dt, self.dev)
         L.gemm(feat, self.mu_w, z, n, 12544, 25088, bias=self.mu_b, eps=eps, eps_c=256, eps_hw=49, mu_out=mu_out,
                ldd=12544, backend=backend)
@@ -465,6 +486,7 @@ class PackedVAE:
         L.gemm(feat, self.var_w, var, n, 12544, 25088, bias=self.var_b, out_f32=self.dt != torch.float32)
         return 0.5 * torch.mean(-0.5 * torch.sum(1 + var - mu ** 2 - var.exp(), dim=1), dim=0)
 
+    @_on_device
     def forward(self, x, eps, want_xhat=False, want_kl=False, backend=L.GEMM_AUTO):
         """GenConViTVAE.forward (genconvit_vae.py:107-116) -> (fp32 logits [N,2], x_hat224 | None, kl | None).
 
@@ -472,6 +494,10 @@ class PackedVAE:
         share one set of GEMM launches over the concatenated tokens."""
         dev, dt = self.dev, self.dt
         n, _, hh, ww = x.shape
+        if (hh, ww) != (224, 224) or x.shape[1] != 3:
+            # the encoder's Linear(128*14*14 -> latent) and the decoder's Unflatten(256,7,7) fix the geometry
+            # (genconvit_vae.py:34-37,64); the reference fails in nn.Linear with a shape error for anything else
+            raise ValueError(f"GenConViTVAE takes [N,3,224,224] frames, got {tuple(x.shape)}")
         feat = self.encode_features(x, backend)
         mu = _empty((n, 12544), torch.float32, dev) if want_kl else None
         z = self.latent(feat, eps, mu, backend)
@@ -503,5 +529,7 @@ def score_videos(logits, n_nets, n_frames, frames_per_video):
     mean = torch.empty((v, 2), dtype=torch.float32, device=dev)
     cls = torch.empty((v,), dtype=torch.int32, device=dev)
     val = torch.empty((v,), dtype=torch.float32, device=dev)
-    L.score_videos(logits, n_nets, n_frames, frames_per_video, mean, cls, val)
+    L.require_cuda_tensor(logits, "score_videos")
+    with torch.cuda.device(dev):
+        L.score_videos(logits, n_nets, n_frames, frames_per_video, mean, cls, val)
     return mean, cls, val

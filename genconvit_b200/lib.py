@@ -114,6 +114,28 @@ def require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise GcvError(f"{what}: tensor is on {t.device}; the GenConViT forward only runs on a CUDA (sm_100a) device "
                        "-- there is no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream (and per-device kernel attributes are set for it): foreign
+        # pointers there fault the GPU.  The model forwards enter torch.cuda.device(x.device) themselves.
+        raise GcvError(f"{what}: tensor is on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                       "wrap the call in torch.cuda.device(tensor.device)")
+
+
+def require_cuda_tensor(t: torch.Tensor, what: str):
+    """Only the is-CUDA half of ``require_cuda`` (the caller switches the current device itself)."""
+    if not t.is_cuda:
+        raise GcvError(f"{what}: tensor is on {t.device}; the GenConViT forward only runs on a CUDA (sm_100a) device "
+                       "-- there is no CPU fallback")
+
+
+def _avail(t: torch.Tensor) -> int:
+    """Elements addressable from ``t.data_ptr()`` to the end of its storage (views / tails of larger buffers)."""
+    return t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()
+
+
+def _need(t, count, what):
+    if _avail(t) < count:
+        raise GcvError(f"{what}: needs {count} elements from the tensor's first element, its storage holds {_avail(t)}")
 
 
 # ---- launch counter (bench.py reports how many of our kernels ran in the timed region) ----
@@ -146,6 +168,19 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     """D[M,N] = epilogue(A[M,K] @ B[N,K]^T); see gcv_gemm / gcv_epilogue."""
     global launches
     require_cuda(a, "gemm")
+    lda_, ldb_ = (lda if lda is not None else K), (ldb if ldb is not None else K)
+    # the C ABI takes raw pointers: reject shapes that would read / write past the tensors (a TMA map over a too-short
+    # buffer is an illegal-address fault, which on a shared box takes the GPU down for everybody)
+    _need(a, (M - 1) * lda_ + K, f"gemm A [{M},{K}] lda={lda_}")
+    _need(b, (N - 1) * ldb_ + K, f"gemm B [{N},{K}] ldb={ldb_}")
+    if store == STORE_ROWS:
+        _need(d, (M - 1) * (ldd if ldd is not None else N) + N, f"gemm D [{M},{N}]")
+    else:
+        _need(d, M * N, f"gemm D (pixel shuffle) [{M},{N}]")
+    if residual is not None:
+        _need(residual, (M - 1) * (ldr if ldr is not None else N) + N, "gemm residual")
+    if eps is not None:
+        _need(eps, M * N, "gemm eps")
     ep = Epilogue()
     ep.bias = bias.data_ptr() if bias is not None else None
     ep.act = act
@@ -164,7 +199,6 @@ def gemm(a, b, d, M, N, K, *, lda=None, ldb=None, ldd=None, bias=None, act=ACT_N
     # [M, chunks, 2] partial sums, or [M, 2] rows already reduced by ln_finalize (ln_chunks = 0)
     ep.ln_chunks = (ln_stats.shape[1] if ln_stats.dim() == 3 else 0) if ln_stats is not None else 0
     ep.ln_eps = ln_eps
-    lda_, ldb_ = (lda if lda is not None else K), (ldb if ldb is not None else K)
     tc = backend == GEMM_TCGEN05 or backend >= 1000 or (
         backend == GEMM_AUTO and a.dtype != torch.float32 and K % 8 == 0 and lda_ % 8 == 0 and ldb_ % 8 == 0
         and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)

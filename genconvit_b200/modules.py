@@ -19,6 +19,21 @@ DEPTHS = engine.DEPTHS
 DIMS = engine.DIMS
 
 
+def weights_fingerprint(module):
+    """Cheap change detector for the kernel-layout weight copies: every in-place write to a parameter or buffer
+    (``load_state_dict`` on this module, a parent or a child, ``copy_``, optimiser steps) bumps its ``_version``;
+    re-allocation (``.to()``, ``.half()``) goes through ``_apply``, which drops the copies anyway."""
+    v = 0
+    n = 0
+    for t in module.parameters():
+        v += t._version
+        n += 1
+    for t in module.buffers():
+        v += t._version
+        n += 1
+    return (n, v)
+
+
 def compute_dtype_of(module: nn.Module, override=None) -> torch.dtype:
     """fp32 parameters -> fp32 kernels (exact mode); .half() -> fp16; .bfloat16() -> bf16.
     ``override`` ('fp32' | 'bf16' | 'fp16' | torch dtype) selects the kernel precision
@@ -90,11 +105,12 @@ class ConvNeXt(nn.Module):
 
     def forward(self, x):
         """fp32 NCHW frames -> fp32 [N,1000] logits, on the CUDA kernels."""
-        L.require_cuda(x, "ConvNeXt.forward")
+        L.require_cuda_tensor(x, "ConvNeXt.forward")
         dt = compute_dtype_of(self, self.compute_dtype)
-        if self._packed is None or self._packed.dt != dt or self._packed.dev != x.device:
+        fp = weights_fingerprint(self)
+        if self._packed is None or self._packed.dt != dt or self._packed.dev != x.device or self._packed_fp != fp:
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith("patch_embed.")}
-            self._packed = engine.PackedConvNeXt(sd, x.device, dt)
+            self._packed, self._packed_fp = engine.PackedConvNeXt(sd, x.device, dt), fp
         return self._packed.forward_images(x.float().contiguous())
 
 
@@ -198,10 +214,11 @@ class SwinTransformer(nn.Module):
 
     def forward(self, x):
         """fp32 NCHW 224x224 frames -> fp32 [N,1000] logits, on the CUDA kernels."""
-        L.require_cuda(x, "SwinTransformer.forward")
+        L.require_cuda_tensor(x, "SwinTransformer.forward")
         dt = compute_dtype_of(self, self.compute_dtype)
-        if self._packed is None or self._packed.dt != dt or self._packed.dev != x.device:
-            self._packed = engine.PackedSwin(self.state_dict(), x.device, dt)
+        fp = weights_fingerprint(self)
+        if self._packed is None or self._packed.dt != dt or self._packed.dev != x.device or self._packed_fp != fp:
+            self._packed, self._packed_fp = engine.PackedSwin(self.state_dict(), x.device, dt), fp
         return self._packed.forward_images(x.float().contiguous())
 
 

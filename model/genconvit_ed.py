@@ -6,14 +6,17 @@ import torch
 import torch.nn as nn
 
 from genconvit_b200 import engine, lib as L
-from genconvit_b200.modules import compute_dtype_of, create_model
+from genconvit_b200.modules import compute_dtype_of, create_model, weights_fingerprint
 
 from .model_embedder import HybridEmbed
 
 
 class _Packable(nn.Module):
-    """Invalidate the kernel-layout weight copies whenever parameters may have changed."""
+    """Invalidate the kernel-layout weight copies whenever parameters may have changed: re-allocation (``.to()``,
+    ``.half()``) through ``_apply``, in-place writes (``load_state_dict`` on this module, a PARENT or a child, direct
+    ``copy_``) through ``weights_fingerprint`` checked on every forward."""
     _packed = None
+    _packed_fp = None
     compute_dtype = None        # None: follow the parameter dtype; or 'fp32' | 'bf16' | 'fp16'
 
     def _apply(self, fn, *a, **k):
@@ -69,13 +72,14 @@ class GenConViTED(_Packable):
 
     def _engine(self, device):
         dt = compute_dtype_of(self, self.compute_dtype)
-        if self._packed is None or self._packed.dt != dt or self._packed.dev != device:
-            self._packed = engine.PackedED(self.state_dict(), device, dt)
+        fp = weights_fingerprint(self)
+        if self._packed is None or self._packed.dt != dt or self._packed.dev != device or self._packed_fp != fp:
+            self._packed, self._packed_fp = engine.PackedED(self.state_dict(), device, dt), fp
         return self._packed
 
     def forward(self, images):
         """[N,3,224,224] -> logits [N,2] (dtype of the parameters, like the reference)."""
-        L.require_cuda(images, "GenConViTED.forward")
+        L.require_cuda_tensor(images, "GenConViTED.forward")
         x = images.float().contiguous()
         logits = self._engine(x.device).forward(x)
         return logits.to(next(self.parameters()).dtype)

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from genconvit_b200 import engine, lib as L
-from genconvit_b200.modules import compute_dtype_of, create_model
+from genconvit_b200.modules import compute_dtype_of, create_model, weights_fingerprint
 
 from .config import load_config
 from .genconvit_ed import _Packable, _chain
@@ -73,12 +73,13 @@ class GenConViTVAE(_Packable):
 
     def _engine(self, device):
         dt = compute_dtype_of(self, self.compute_dtype)
-        if self._packed is None or self._packed.dt != dt or self._packed.dev != device:
-            self._packed = engine.PackedVAE(self.state_dict(), device, dt, with_var=self.compute_kl)
+        fp = (weights_fingerprint(self), bool(self.compute_kl))      # toggling compute_kl re-packs (the var weights)
+        if self._packed is None or self._packed.dt != dt or self._packed.dev != device or self._packed_fp != fp:
+            self._packed, self._packed_fp = engine.PackedVAE(self.state_dict(), device, dt, with_var=self.compute_kl), fp
         return self._packed
 
     def _forward(self, x, eps=None, want_xhat=True):
-        L.require_cuda(x, "GenConViTVAE.forward")
+        L.require_cuda_tensor(x, "GenConViTVAE.forward")
         x = x.float().contiguous()
         eps = eps if eps is not None else self._eps
         if eps is None:

@@ -52,7 +52,8 @@ def test_gemm_tcgen05_plain(shape, dtype):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(128 * 300 + 7, 384, 1536), (128 * 296, 768, 512), (128 * 311 + 100, 384, 768)])
 def test_gemm_tcgen05_wide_pair_tiles(shape, dtype):
-    """Large-K, N = 384k contractions run as 256 x 384 cta_group::2 tiles (two N=192 MMAs, one TMEM stage)."""
+    """256 x 384 cta_group::2 tiles (two N=192 MMAs side by side, one TMEM stage).  The auto-tuner prefers two 192-wide
+    tiles, so the path is FORCED here with backend = 1000 + 384 (the tile-width test hook of gcv_gemm)."""
     L = _lib()
     M, N, K = shape
     a, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
@@ -60,11 +61,11 @@ def test_gemm_tcgen05_wide_pair_tiles(shape, dtype):
     res = _rand(M, N, dtype=dtype, seed=5)
     want = res.float() + gamma * (a.float() @ b.float().t() + bias)
     d = res.clone()
-    L.gemm(a, b, d, M, N, K, bias=bias, gamma=gamma, residual=d, ldr=N)
+    L.gemm(a, b, d, M, N, K, bias=bias, gamma=gamma, residual=d, ldr=N, backend=1000 + 384)
     torch.cuda.synchronize()
     _close(d, want, TOL[dtype], f"wide tiles {shape}")
     d32 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
-    L.gemm(a, b, d32, M, N, K, out_f32=True)
+    L.gemm(a, b, d32, M, N, K, out_f32=True, backend=1000 + 384)
     torch.cuda.synchronize()
     _close(d32, a.float() @ b.float().t(), 1e-4, f"wide tiles fp32 out {shape}")
 
@@ -92,10 +93,10 @@ def test_gemm_tcgen05_many_tiles_persistent():
 
 
 @pytest.mark.parametrize("shape", [(40000, 512, 512), (148 * 128 * 2 + 128 * 3 + 5, 384, 1536), (20000, 1536, 384)])
-def test_gemm_tcgen05_pair_mode_multicast(shape, monkeypatch):
-    """Opt-in pair mode: 2-CTA clusters that share the B tile by TMA multicast (odd M-tile counts included).
-    GCV_GEMM_PAIR is read once per process, so this test is only meaningful when it runs with the variable set
-    (tools/run_pair_tests.sh); otherwise it exercises the default path on the same shapes."""
+def test_gemm_tcgen05_cta_pair_tiles(shape):
+    """cta_group::2 pair tiles (256 x block_n, each CTA stages its own A rows and half of B) -- the mode every large
+    contraction takes (>= 2 waves of tiles, K >= 256) -- including an odd number of 128-row tiles, where the second
+    CTA of the last pair works on a tile that lies entirely past M."""
     L = _lib()
     M, N, K = shape
     a, b = _rand(M, K, dtype=torch.bfloat16, seed=7), _rand(N, K, dtype=torch.bfloat16, seed=8, scale=K ** -0.5)

@@ -115,15 +115,13 @@ def test_vae_kl_side_effect(vae_model, golden):
     x = synthetic_frames(g["n"], g["frames_seed"]).to(DEV)
     eps = synthetic_eps(g["n"], g["eps_seed"]).to(DEV)
     vae_model.set_compute_dtype("fp32")
-    vae_model.compute_kl = True
-    vae_model._packed = None
+    vae_model.compute_kl = True          # part of the packed-weight cache key: the var weights are packed on demand
     try:
         with torch.no_grad():
             vae_model(x, eps=eps)
         assert abs(float(vae_model.encoder.kl) - float(g["kl"])) <= 1e-4 * abs(float(g["kl"]))
     finally:
         vae_model.compute_kl = False
-        vae_model._packed = None
 
 
 def test_vae_default_eps_is_stochastic_like_the_reference(vae_model):
@@ -216,6 +214,114 @@ def test_bs256_fp16_properties(full_model):
             full_model.model_vae.set_epsilon(None)
     assert cls.shape == (n // fpv,)
     assert int(cls[2]) == c1 and abs(float(val[2]) - v1) <= 5e-3
+
+
+# --------------------------------------------------------------------------- the benchmarked size, against the oracle
+BS256_FPV = 16          # bench.py scores 16 videos x 16 frames per 256-frame step
+
+
+@pytest.fixture(scope="module")
+def oracle_bs256(sd_ed, sd_vae):
+    """The CPU oracle on 256 frames (BASELINE config 2 size), computed once per test session in 32-frame chunks:
+    (frames, eps, ED logits [256,2], VAE logits [256,2])."""
+    from oracle import nets
+    from oracle.weights import synthetic_eps, synthetic_frames
+    x, eps = synthetic_frames(256, 81), synthetic_eps(256, 82)
+    ed, vae = [], []
+    with torch.no_grad():
+        for i in range(0, 256, 32):
+            ed.append(nets.ed_forward(sd_ed, x[i:i + 32]))
+            vae.append(nets.vae_forward(sd_vae, x[i:i + 32], eps[i:i + 32], resize=False)[0])
+    return x, eps, torch.cat(ed), torch.cat(vae)
+
+
+def _check_rows_and_videos(rows, want, what, fpv=BS256_FPV):
+    """[R,2] logits vs the oracle: BASELINE tolerance, identical per-frame decision, and the per-video pred_vid tuple
+    (model/pred_func.py:111-131) of every ``fpv``-frame video."""
+    from oracle import nets
+    err = (rows - want).abs().max().item()
+    assert err <= 2e-2, f"{what}: max|dlogit| = {err:.3e} over {rows.shape[0]} rows"
+    flips = (rows.argmax(1) != want.argmax(1)).nonzero().flatten().tolist()
+    assert not flips, f"{what}: per-frame decision differs on rows {flips[:8]}"
+    return err
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_full_bs256_matches_oracle(full_model, oracle_bs256, mode):
+    """BASELINE config 2 / north-star size: full GenConViT (ED + VAE) at bs = 256 in fp16 AND bf16 against the CPU
+    oracle on the same frames / eps -- the [512,2] rows, every per-frame decision and the 16 per-video pred_vid tuples.
+    This is the batch size at which the cta_group::2 pair tiles (tiles >= 2 x SMs) and the single-round `mu`
+    weight-streaming tiles (tiles_m == 2) switch on."""
+    from model import pred_func
+    from oracle import nets
+    x, eps, ed, vae = oracle_bs256
+    want = torch.cat((ed, vae))
+    full_model.set_compute_dtype(mode)
+    full_model.model_vae.set_epsilon(eps.to(DEV))
+    try:
+        with torch.no_grad():
+            rows = full_model(x.to(DEV)).float().cpu()
+            cls, val = pred_func.pred_videos(x.to(DEV), full_model, BS256_FPV)
+    finally:
+        full_model.model_vae.set_epsilon(None)
+    assert rows.shape == (512, 2)
+    err = _check_rows_and_videos(rows, want, f"full bs256 {mode}")
+    err_ed, err_vae = (rows[:256] - ed).abs().max().item(), (rows[256:] - vae).abs().max().item()
+    print(f"bs256 {mode}: max|dlogit| ED {err_ed:.3e} VAE {err_vae:.3e}")
+    for v in range(256 // BS256_FPV):
+        sl = slice(v * BS256_FPV, (v + 1) * BS256_FPV)
+        c_want, v_want = nets.pred_vid(torch.cat((ed[sl], vae[sl])))
+        assert abs(float(val[v]) - v_want) <= 5e-3, f"video {v}: score {float(val[v])} vs {v_want}"
+        m = torch.sigmoid(torch.cat((ed[sl], vae[sl]))).mean(0)
+        if abs(float(m[0] - m[1])) > 1e-2:              # a video whose two class means tie to 1e-2 may legitimately flip
+            assert int(cls[v]) == c_want, f"video {v}: class {int(cls[v])} vs {c_want}"
+    assert err <= 2e-2
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_vae_bs256_matches_oracle(vae_model, oracle_bs256, mode):
+    """Network B alone at bs = 256: M = 256 is exactly one CTA pair of rows, i.e. the `mu` layer (K = 25088,
+    N = 12544) runs on the single-round weight-streaming pair tiles (gemm_tcgen05.cu, stream_b)."""
+    x, eps, _, vae = oracle_bs256
+    vae_model.set_compute_dtype(mode)
+    with torch.no_grad():
+        got = vae_model._forward(x.to(DEV), eps.to(DEV), want_xhat=False)[0].float().cpu()
+    _check_rows_and_videos(got, vae, f"VAE bs256 {mode}")
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_ed_bs256_matches_oracle(ed_model, oracle_bs256, mode):
+    x, _, ed, _ = oracle_bs256
+    ed_model.set_compute_dtype(mode)
+    with torch.no_grad():
+        got = ed_model(x.to(DEV)).float().cpu()
+    _check_rows_and_videos(got, ed, f"ED bs256 {mode}")
+
+
+def test_packed_weights_follow_parent_load_state_dict_and_inplace_edits(sd_ed):
+    """nn.Module.load_state_dict on a PARENT never calls the child's load_state_dict, and in-place parameter edits call
+    nothing at all: the kernel-layout weight copies must still be rebuilt (fingerprint of parameter versions)."""
+    from model.genconvit import GenConViT
+    from model.genconvit_ed import GenConViTED
+    from oracle.weights import make_state_dict, synthetic_frames
+    ed = GenConViTED(_config()).eval()
+    ed.load_state_dict(sd_ed, strict=True)
+    wrapper = GenConViT.from_modules(model_ed=ed).to(DEV)
+    wrapper.set_compute_dtype("fp16")
+    x = synthetic_frames(2, 91).to(DEV)
+    with torch.no_grad():
+        a = wrapper(x).clone()
+        other = make_state_dict("ed", 5)
+        wrapper.load_state_dict({"model_ed." + k: v for k, v in other.items()}, strict=True)   # parent-level load
+        b = wrapper(x).clone()
+        assert not torch.equal(a, b), "stale packed weights after a parent load_state_dict"
+        ed2 = GenConViTED(_config()).eval()
+        ed2.load_state_dict(other, strict=True)
+        ed2.to(DEV).set_compute_dtype("fp16")
+        assert torch.equal(b, ed2(x))
+        wrapper.model_ed.fc2.bias.add_(1.0)                                                     # in-place edit
+        c = wrapper(x)
+        assert (c - b - 1.0).abs().max().item() <= 2e-3
 
 
 def test_cuda_graph_replay_matches_eager(ed_model):

@@ -43,6 +43,16 @@ if args.which in ("dwconv", "all"):
               2.0 * x.numel() * 2 / 1e3, "TB/s")
         timed(f"  layernorm_rows only B{B} H{H} C{C}", lambda: L.layernorm_rows(y, y, lw, lb, 1e-6, B * H * H, C),
               2.0 * x.numel() * 2 / 1e3, "TB/s")
+if args.which in ("dwstats", "all"):
+    # the tensor-core depthwise kernel as the 16-bit forward calls it (un-normalised output + LayerNorm partial sums)
+    for (H, C, mult) in ((56, 96, 2), (28, 192, 2), (14, 384, 2), (7, 768, 2), (28, 96, 1), (14, 192, 1)):
+        Bn = B * mult
+        x = torch.randn(Bn, H, H, C, device=dev).to(dt)
+        y = torch.empty_like(x)
+        stats = torch.empty(Bn * H * H, C // 32, 2, device=dev)
+        taps, bias = torch.randn(49, C, device=dev) / 7, torch.randn(C, device=dev)
+        timed(f"dwconv7_stats B{Bn} H{H} C{C}", lambda: L.dwconv7_stats(x, y, stats, taps, bias, Bn, H, H, C),
+              2.0 * x.numel() * 2 / 1e3, "TB/s")
 if args.which in ("fc1", "all"):
     for (T, C) in ((3136, 96), (784, 192), (196, 384), (49, 768)):
         M = B * T
