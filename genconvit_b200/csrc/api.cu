@@ -72,6 +72,7 @@ int resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, in
 int nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* mean_out, int32_t* cls_out,
                  float* val_out, cudaStream_t stream);
+int score_videos_pair(const float* la, const float* lb, int n_frames, int fpv, float* out, cudaStream_t stream);
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
 int swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C, int heads,
@@ -236,6 +237,10 @@ int gcv_preprocess_frames(const uint8_t* x, float* y, int N, int H, int W, const
 int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video, float* mean_out,
                      int32_t* cls_out, float* val_out, void* stream) {
   return score_videos(logits, n_nets, n_frames, frames_per_video, mean_out, cls_out, val_out, S(stream));
+}
+int gcv_score_videos_pair(const float* logits_ed, const float* logits_vae, int n_frames, int frames_per_video, float* out,
+                          void* stream) {
+  return score_videos_pair(logits_ed, logits_vae, n_frames, frames_per_video, out, S(stream));
 }
 
 }  // extern "C"

@@ -283,6 +283,32 @@ score_videos_kernel(const float* __restrict__ logits, int n_nets, int n_frames, 
 }
 
 
+// one warp per video; rows of the ED and of the VAE network are read from their own buffers (either may be null)
+__global__ void __launch_bounds__(32)
+score_videos_pair_kernel(const float* __restrict__ la, const float* __restrict__ lb, int n_videos, int fpv,
+                         float* __restrict__ out) {
+  const int v = blockIdx.x, lane = threadIdx.x;
+  float s0 = 0.0f, s1 = 0.0f;
+  int rows = 0;
+#pragma unroll
+  for (int net = 0; net < 2; ++net) {
+    const float* lg = net == 0 ? la : lb;
+    if (!lg) continue;
+    rows += fpv;
+    for (int f = lane; f < fpv; f += 32) {
+      const float2 l = *reinterpret_cast<const float2*>(lg + 2 * ((int64_t)v * fpv + f));
+      s0 += 1.0f / (1.0f + expf(-l.x));
+      s1 += 1.0f / (1.0f + expf(-l.y));
+    }
+  }
+  s0 = warp_sum(s0) / (float)rows;
+  s1 = warp_sum(s1) / (float)rows;
+  if (lane == 0) {
+    out[v] = s1 > s0 ? 1.0f : 0.0f;                             // torch.argmax: first maximal index on ties
+    out[n_videos + v] = s0 > s1 ? s0 : fabsf(1.0f - s1);        // ties take the else branch (pred_func.py:128-130)
+  }
+}
+
 // ---- first 3x3 conv on the tensor cores (16-bit modes) -----------------------------------------------------------
 // The FFMA kernel above needs 432 FMAs per conv pixel and is issue-bound at ~1 TB/s.  Here the frame tile is staged
 // once in shared memory as 16-bit RGB0 pixels (8 B each, zero outside the image = the conv padding) and the conv runs
@@ -540,6 +566,14 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
               "score_videos: n_frames (%d) must be a positive multiple of frames_per_video (%d)", n_frames, fpv);
   score_videos_kernel<<<n_frames / fpv, 32, 0, stream>>>(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out);
   return check_launch("score_videos");
+}
+
+int score_videos_pair(const float* la, const float* lb, int n_frames, int fpv, float* out, cudaStream_t stream) {
+  GCV_REQUIRE((la || lb) && out, "score_videos_pair: null pointer");
+  GCV_REQUIRE(fpv > 0 && n_frames >= fpv && n_frames % fpv == 0,
+              "score_videos_pair: n_frames (%d) must be a positive multiple of frames_per_video (%d)", n_frames, fpv);
+  score_videos_pair_kernel<<<n_frames / fpv, 32, 0, stream>>>(la, lb, n_frames / fpv, fpv, out);
+  return check_launch("score_videos_pair");
 }
 
 }  // namespace gcv

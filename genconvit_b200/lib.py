@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -82,6 +82,7 @@ def load():
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_score_videos.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.gcv_score_videos_pair.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.gcv_swin_window_attention.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.gcv_swin_patch_merge.argtypes = [i32, vp, vp, i32, i32, i32, vp]
     lib.gcv_mean_tokens.argtypes = [i32, vp, vp, i32, i32, i32, vp]
@@ -90,7 +91,7 @@ def load():
         fn = getattr(lib, name)
         if name not in ("gcv_last_error",):
             fn.restype = C.c_int
-    if lib.gcv_abi_version() != 2:
+    if lib.gcv_abi_version() != 3:
         raise GcvError("libgenconvit_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -373,3 +374,16 @@ def score_videos(logits, n_nets, n_frames, fpv, mean_out, cls_out, val_out):
     require_cuda(logits, "score_videos")
     _run("score_videos", 8.0 * n_nets * n_frames, lambda: load().gcv_score_videos(
         _p(logits), n_nets, n_frames, fpv, _p(mean_out), _p(cls_out), _p(val_out), _stream()))
+
+
+def score_videos_pair(logits_ed, logits_vae, n_frames, fpv, out):
+    """pred_vid scoring straight from the ED / VAE logit buffers (either may be None) into fp32 out[2, V]."""
+    ref = logits_ed if logits_ed is not None else logits_vae
+    require_cuda(ref, "score_videos_pair")
+    for t in (logits_ed, logits_vae):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            _need(t, 2 * n_frames, "score_videos_pair logits")
+    _need(out, 2 * (n_frames // fpv), "score_videos_pair out")
+    _run("score_videos", 8.0 * n_frames * ((logits_ed is not None) + (logits_vae is not None)),
+         lambda: load().gcv_score_videos_pair(_p(logits_ed), _p(logits_vae), n_frames, fpv, _p(out), _stream()))

@@ -16,11 +16,20 @@ from . import engine
 from . import lib as L
 
 
+_MEAN = (0.485, 0.456, 0.406)     # reference dataset/loader.py:64-65 (normalize_data()["vid"]), as in model.pred_func
+_STD = (0.229, 0.224, 0.225)
+
+
 class VideoScorer:
     def __init__(self, model, batch_frames, frames_per_video, eps=None, use_graph=True, img=224):
         """model: model.genconvit.GenConViT on a CUDA device; batch_frames: frames per step (whole
         videos: a multiple of frames_per_video).  eps: None -> fresh N(0,1) noise every step like
-        the reference (genconvit_vae.py:46); or a fixed [batch_frames,12544] tensor."""
+        the reference (genconvit_vae.py:46); or a fixed [batch_frames,12544] tensor.
+
+        ``submit`` takes either the reference's pre-processed frames (fp32 NCHW, model/pred_func.py:95-108) or the raw
+        uint8 NHWC face crops that function starts from; the latter cross PCIe at a quarter of the bytes and are
+        normalised on the GPU (``gcv_preprocess_frames``, bit-identical to the host arithmetic) straight into the
+        graph's input buffer."""
         if batch_frames % frames_per_video:
             raise ValueError("batch_frames must hold whole videos")
         self.model = model
@@ -29,8 +38,11 @@ class VideoScorer:
         self.n_videos = batch_frames // frames_per_video
         self.n_nets = 1 if model.net in ("ed", "vae") else 2
         dev = self.dev
-        self.x_stage = torch.empty((batch_frames, 3, img, img), dtype=torch.float32, device=dev)
-        self.x_static = torch.empty_like(self.x_stage)
+        self.img = img
+        self.x_static = torch.empty((batch_frames, 3, img, img), dtype=torch.float32, device=dev)
+        self.x_stage = None                  # fp32 staging buffer, allocated on the first fp32 submit
+        self.u8_stage = [None, None]         # uint8 NHWC staging buffers (double-buffered), on the first uint8 submit
+        self.u8_turn = 0
         self.has_vae = model.net != "ed"
         self.fixed_eps = eps is not None
         self.eps = (eps.to(dev, torch.float32).contiguous() if eps is not None
@@ -38,6 +50,7 @@ class VideoScorer:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ev_h2d = torch.cuda.Event()
         self.ev_stage_free = torch.cuda.Event()
+        self.ev_u8_free = [torch.cuda.Event(), torch.cuda.Event()]
         self.graph = None
         self.launches_per_step = 0
         self.out = None                      # [2, V] fp32 on device: row 0 = class, row 1 = score
@@ -47,12 +60,13 @@ class VideoScorer:
     def _step(self):
         if self.has_vae and not self.fixed_eps:
             self.eps.normal_()
-        logits = self.model(self.x_static, eps=self.eps).float().contiguous()
-        mean, cls, val = engine.score_videos(logits, self.n_nets, self.n, self.fpv)
+        x1, x2 = self.model.forward_parts(self.x_static, self.eps)
         if self.out is None:
-            self.out = torch.empty((2, self.n_videos), dtype=torch.float32, device=self.dev)
-        self.out[0].copy_(cls)
-        self.out[1].copy_(val)
+            self.out = torch.empty((2, self.n_videos), dtype=torch.float32, device=self.dev)   # row 0 class, row 1 score
+        # fused scoring straight from the two logit buffers: no torch.cat, no per-row copies -- the step launches only
+        # this library's kernels (plus the eps generator)
+        with torch.cuda.device(self.dev):
+            L.score_videos_pair(x1, x2, self.n, self.fpv, self.out)
 
     def _prepare(self, use_graph):
         with torch.no_grad():
@@ -81,22 +95,44 @@ class VideoScorer:
 
     def submit(self, frames_host, out_host):
         """Enqueue one batch: pinned-host frames -> device, forward + scoring, results -> pinned host.
-        Asynchronous; overlaps this batch's H2D with the previous batch's compute."""
+        Asynchronous; overlaps this batch's H2D with the previous batch's compute.
+
+        frames_host: uint8 [N,H,W,3] face crops (preferred: 1 byte per value over PCIe, normalised on the GPU into the
+        graph's input buffer) or fp32 [N,3,H,W] already pre-processed like model.pred_func.preprocess_frame."""
         cur = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.ev_stage_free)
-            self.x_stage.copy_(frames_host, non_blocking=True)
-            self.ev_h2d.record(self.copy_stream)
-        cur.wait_event(self.ev_h2d)
-        self.x_static.copy_(self.x_stage, non_blocking=True)
-        self.ev_stage_free.record(cur)
+        if frames_host.dtype == torch.uint8:
+            if tuple(frames_host.shape) != (self.n, self.img, self.img, 3):
+                raise ValueError(f"uint8 frames must be [{self.n},{self.img},{self.img},3], got {tuple(frames_host.shape)}")
+            i = self.u8_turn
+            self.u8_turn ^= 1
+            if self.u8_stage[i] is None:
+                self.u8_stage[i] = torch.empty((self.n, self.img, self.img, 3), dtype=torch.uint8, device=self.dev)
+                self.ev_u8_free[i].record(cur)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.ev_u8_free[i])          # the preprocess kernel that last read it is done
+                self.u8_stage[i].copy_(frames_host, non_blocking=True)
+                self.ev_h2d.record(self.copy_stream)
+            cur.wait_event(self.ev_h2d)
+            with torch.cuda.device(self.dev):
+                L.preprocess_frames(self.u8_stage[i], self.x_static, self.n, self.img, self.img, _MEAN, _STD)
+            self.ev_u8_free[i].record(cur)
+        else:
+            if self.x_stage is None:
+                self.x_stage = torch.empty_like(self.x_static)
+                self.ev_stage_free.record(cur)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.ev_stage_free)
+                self.x_stage.copy_(frames_host, non_blocking=True)
+                self.ev_h2d.record(self.copy_stream)
+            cur.wait_event(self.ev_h2d)
+            self.x_static.copy_(self.x_stage, non_blocking=True)
+            self.ev_stage_free.record(cur)
         self.run_resident()
         out_host.copy_(self.out, non_blocking=True)
 
     def score(self, frames_host):
         """Synchronous convenience: -> (classes [V] int64, scores [V] float32) on the host."""
         out = torch.empty((2, self.n_videos), dtype=torch.float32).pin_memory()
-        self.ev_stage_free.record(torch.cuda.current_stream(self.dev))
         self.submit(frames_host, out)
         torch.cuda.current_stream(self.dev).synchronize()
         return out[0].to(torch.int64), out[1].clone()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GCV_ABI_VERSION 2
+#define GCV_ABI_VERSION 3
 
 enum gcv_dtype { GCV_F32 = 0, GCV_BF16 = 1, GCV_F16 = 2 };
 enum gcv_act { GCV_ACT_NONE = 0, GCV_ACT_GELU = 1, GCV_ACT_RELU = 2, GCV_ACT_LEAKY = 3 };
@@ -217,6 +217,14 @@ int gcv_preprocess_frames(const uint8_t* x, float* y, int N, int H, int W, const
  */
 int gcv_score_videos(const float* logits, int n_nets, int n_frames, int frames_per_video,
                      float* mean_out, int32_t* cls_out, float* val_out, void* stream);
+
+/* The same scoring straight from the two networks' logit buffers, for the bulk runtime: no concatenation of the
+ * ED and VAE rows (reference model/genconvit.py:74 torch.cat) and one packed result for a single device->host copy.
+ *   logits_ed, logits_vae  fp32 [n_frames,2] each; either may be NULL (single-network model)
+ *   out                    fp32 [2][n_videos]: row 0 = class (0.0 / 1.0), row 1 = score; same tie rules as above
+ * (reference model/pred_func.py:111-131: sigmoid, mean over the video's rows of both networks, argmax, score). */
+int gcv_score_videos_pair(const float* logits_ed, const float* logits_vae, int n_frames, int frames_per_video,
+                          float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,29 @@ class GenConViT(nn.Module):
                 m.set_compute_dtype(dt)
         return self
 
+    def forward_parts(self, x, eps=None):
+        """The two networks' fp32 logits (ED [N,2] | None, VAE [N,2] | None) without the reference's concatenation:
+        the bulk runtime scores straight from both buffers (gcv_score_videos_pair).  ``x``: fp32 NCHW on the GPU."""
+        x1 = x2 = None
+        two = self.net not in ("ed", "vae")
+        if two and _TWO_STREAMS:
+            cur = torch.cuda.current_stream(x.device)
+            side = getattr(self, "_side_stream", None)
+            if side is None or side.device != x.device:
+                side = self._side_stream = torch.cuda.Stream(device=x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                x2 = self.model_vae._logits_f32(x, eps)
+            x1 = self.model_ed._logits_f32(x)
+            cur.wait_stream(side)
+            x2.record_stream(cur)
+            return x1, x2
+        if self.net != "vae":
+            x1 = self.model_ed._logits_f32(x)
+        if self.net != "ed":
+            x2 = self.model_vae._logits_f32(x, eps)
+        return x1, x2
+
     def forward(self, x, eps=None):
         """'ed' -> [N,2]; 'vae' -> [N,2]; otherwise ED rows then VAE rows -> [2N,2] (reference :66-75).
         The VAE's returned image is discarded by the reference here, so it is not computed."""

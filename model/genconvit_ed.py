@@ -77,6 +77,10 @@ class GenConViTED(_Packable):
             self._packed, self._packed_fp = engine.PackedED(self.state_dict(), device, dt), fp
         return self._packed
 
+    def _logits_f32(self, x):
+        """fp32 contiguous NCHW frames on the GPU -> the engine's fp32 logits [N,2] (no dtype round trip)."""
+        return self._engine(x.device).forward(x)
+
     def forward(self, images):
         """[N,3,224,224] -> logits [N,2] (dtype of the parameters, like the reference)."""
         L.require_cuda_tensor(images, "GenConViTED.forward")

@@ -78,6 +78,13 @@ class GenConViTVAE(_Packable):
             self._packed, self._packed_fp = engine.PackedVAE(self.state_dict(), device, dt, with_var=self.compute_kl), fp
         return self._packed
 
+    def _logits_f32(self, x, eps=None):
+        """fp32 contiguous NCHW frames (+ fp32 eps [N,latent] or None) on the GPU -> the engine's fp32 logits [N,2]."""
+        eps = eps if eps is not None else self._eps
+        if eps is None:
+            eps = torch.randn(x.shape[0], self.latent_dims, device=x.device, dtype=torch.float32)
+        return self._engine(x.device).forward(x, eps, want_xhat=False, want_kl=False)[0]
+
     def _forward(self, x, eps=None, want_xhat=True):
         L.require_cuda_tensor(x, "GenConViTVAE.forward")
         x = x.float().contiguous()

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(dll, s), f"{s} declared in the header but not exported"
     assert sorted(lib.EXPORTS) == syms
     dll.gcv_abi_version.restype = ctypes.c_int
-    assert dll.gcv_abi_version() == 2
+    assert dll.gcv_abi_version() == 3
 
 
 def test_epilogue_struct_matches_header_layout():
