@@ -17,7 +17,17 @@
 //             16-bit pack, swizzled st.shared into H (then fence.proxy.async + mbarrier arrive); per tile, the
 //             O accumulator goes through the same bias / layer-scale / residual / staged coalesced store path as
 //             the stand-alone GEMM.
-// TMEM: S0 [0,128), S1 [128,256), O [256, 256+C).
+// TMEM: S0 [0,128), S1 [128,256), H [256,320), O0 [320, 320+C) (, O1 [320+C, 320+2C) for C = 96).
+//
+// Second generation (what the first version's profile showed: l1tex 70 % busy, tensor pipe 25 % -- per 128-row tile the
+// kernel moved ~730 KB through shared memory: weights re-streamed by TMA for every tile, both operands of every MMA,
+// the GELU output written by st.shared and read back by the MMA):
+//   * the GELU output H never touches shared memory: the epilogue warps write it to TENSOR memory (tcgen05.st, two
+//     16-bit values per 32-bit column, lane = row) and fc2 takes it as its A operand from there (tcgen05.mma with
+//     A in TMEM) -- no st.shared of H, no A-operand reads for fc2;
+//   * C = 96: W1 and W2 (147 KB) are loaded ONCE per CTA and stay resident in shared memory; only the y block of the
+//     next tile (double-buffered) is streamed.  C = 192 keeps streaming its 590 KB of weights through the slot ring,
+//     which the freed H buffers make deeper.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -41,22 +51,28 @@ struct Cfg {
   static constexpr int XKB = C / FKB;                        // K-blocks of y / W1 (3 / 6)
   static constexpr int HKB = FCH / FKB;                      // K-blocks of H / W2 (4)
   static constexpr int X_BYTES = XKB * FBLK;
-  static constexpr int H_BYTES = HKB * FBLK;
-  // ring slot = 24 KB of weights: 3 K-blocks of W1 (128 hidden rows x 64 B each) or KB2 K-blocks of W2 (C rows x 64 B
-  // each); one mbarrier wait per slot keeps the single MMA-issuing thread off the critical path
+  // C = 96: both weight matrices resident in shared memory for the whole launch
+  static constexpr bool RESIDENT = C <= 96;
+  static constexpr int W1_CHUNK = XKB * FBLK;                // one 128-row hidden chunk of W1: XKB K-blocks of 128 x 64 B
+  static constexpr int W2_CHUNK = HKB * C * 64;              // the matching K = 128 slab of W2: 4 K-blocks of C x 64 B
+  static constexpr int W_BYTES = RESIDENT ? NCH * (W1_CHUNK + W2_CHUNK) : 0;
+  // streamed weights (C = 192): ring slot = 24 KB: 3 K-blocks of W1 (128 hidden rows x 64 B each) or KB2 K-blocks of W2
+  // (C rows x 64 B each); one mbarrier wait per slot keeps the single MMA-issuing thread off the critical path
   static constexpr int SLOT = 3 * FBLK;
   static constexpr int KB1 = 3, P1 = XKB / KB1;              // W1 chunk = P1 slots
   static constexpr int KB2 = SLOT / (C * 64), P2 = HKB / KB2; // W2 chunk = P2 slots
+  static constexpr int RING = RESIDENT ? 0 : 5;
   // the chunk pipeline runs across tile boundaries: that needs the next tile's y block and (TMEM permitting) a
   // second output accumulator
-  static constexpr int XBUF = 1;   // fc1 runs two chunks ahead, which hides the reload of the single y buffer
-  static constexpr int OBUF = (2 * FCH + 2 * C <= 512) ? 2 : 1;
-  static constexpr int RING = C <= 96 ? 4 : 3;
-  static constexpr int STAGE_BYTES = kFEpiWarps * 32 * 64;   // per-warp 32 x 64 B output staging tiles
+  static constexpr int XBUF = RESIDENT ? 2 : 1;  // streamed weights: fc1 runs two chunks ahead, which hides the reload of the single y buffer
+  static constexpr int OBUF = (2 * FCH + FCH / 2 + 2 * C <= 512) ? 2 : 1;
+  static constexpr int STAGE_WARPS = 4 * (C / 32 < 4 ? C / 32 : 4);     // epilogue warps that drain output columns
+  static constexpr int STAGE_BYTES = STAGE_WARPS * 32 * 64;  // per-warp 32 x 64 B output staging tiles
   static constexpr int VEC_BYTES = ((2 * HC + 2 * C) * 4 + 1023) / 1024 * 1024;   // b1, colsum1 (LN fold), b2, gamma
-  static constexpr int SMEM = kFCtrl + VEC_BYTES + XBUF * X_BYTES + 2 * H_BYTES + RING * SLOT + STAGE_BYTES + 1024;
+  static constexpr int SMEM = kFCtrl + VEC_BYTES + XBUF * X_BYTES + W_BYTES + RING * SLOT + STAGE_BYTES + 1024;
   static_assert(C % 32 == 0 && C <= 192 && HC % FCH == 0 && NCH >= 2, "unsupported width");
   static_assert(XKB % KB1 == 0 && KB2 * C * 64 == SLOT && HKB % KB2 == 0, "slot geometry");
+  static_assert(2 * FCH + FCH / 2 + OBUF * C <= 512, "tensor memory budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -89,11 +105,32 @@ __device__ long long gcv_fused_trace[64];
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// tcgen05.mma with the A operand in tensor memory (16-bit elements, two per 32-bit column, lane = row)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this warp's 32 lanes
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+      "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <typename T, int C, bool LN>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const FParams p) {
   using K = Cfg<C>;
+  constexpr int NRING = K::RING > 0 ? K::RING : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -105,20 +142,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   uint64_t* o_empty = bars + 6;       // [2]
   uint64_t* s_full = bars + 8;        // [2]
   uint64_t* s_empty = bars + 10;      // [2]
-  uint64_t* h_full = bars + 12;       // [2]
-  uint64_t* h_empty = bars + 14;      // [2]
+  uint64_t* h_full = bars + 12;       // [1]  the single H buffer in tensor memory: chunk g's GELU output is in place
+  uint64_t* h_empty = bars + 13;      // [2]  fc2 of chunk g has read it: barrier g & 1 (each epilogue group then waits on
+                                      //      consecutive phases of ONE barrier -- parity waits must not skip a phase)
+  uint64_t* w_full = bars + 15;       // [1]  resident weights have landed
   uint64_t* ring_full = bars + 16;    // [RING]
-  uint64_t* ring_empty = bars + 16 + K::RING;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * K::RING);
+  uint64_t* ring_empty = bars + 16 + NRING;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * NRING);
   float* vec_b1 = reinterpret_cast<float*>(gbase + kFCtrl);           // [HC]
   float* vec_s1 = vec_b1 + K::HC;                                      // [HC] column sums of W1 (LN fold)
   float* vec_b2 = vec_s1 + K::HC;                                      // [C]
   float* vec_g = vec_b2 + C;                                           // [C]
   const uint32_t x_smem = base + kFCtrl + K::VEC_BYTES;               // X0 (, X1)
-  const uint32_t h_smem = x_smem + K::XBUF * K::X_BYTES;              // H0, H1
-  const uint32_t ring_smem = h_smem + 2 * K::H_BYTES;
-  uint8_t* h_gen = gbase + kFCtrl + K::VEC_BYTES + K::XBUF * K::X_BYTES;   // generic pointer to H0
-  uint8_t* stage_gen = h_gen + 2 * K::H_BYTES + K::RING * K::SLOT;          // output staging, one 2 KB tile per warp
+  const uint32_t w_smem = x_smem + K::XBUF * K::X_BYTES;              // resident: W1 chunks, then W2 chunks
+  const uint32_t ring_smem = w_smem + K::W_BYTES;
+  uint8_t* stage_gen = gbase + kFCtrl + K::VEC_BYTES + K::XBUF * K::X_BYTES + K::W_BYTES + K::RING * K::SLOT;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (tc_ptx.cuh elect_one)
   const int lane = threadIdx.x & 31;
@@ -133,9 +171,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       mbar_init(smem_u32(o_empty + i), kFEpiWarps);
       mbar_init(smem_u32(s_full + i), 1);
       mbar_init(smem_u32(s_empty + i), kFEpiWarps / 2);     // chunk buffer i belongs to epilogue group i (8 warps)
-      mbar_init(smem_u32(h_full + i), kFEpiWarps / 2);
-      mbar_init(smem_u32(h_empty + i), 1);
     }
+    mbar_init(smem_u32(h_full), kFEpiWarps / 2);            // the group that owns the chunk
+    mbar_init(smem_u32(h_empty + 0), 1);
+    mbar_init(smem_u32(h_empty + 1), 1);
+    mbar_init(smem_u32(w_full), 1);
     for (int i = 0; i < K::RING; ++i) {
       mbar_init(smem_u32(ring_full + i), 1);
       mbar_init(smem_u32(ring_empty + i), 1);
@@ -160,22 +200,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 2 * FCH;      // O0 (, O1 = O0 + C)
+  const uint32_t tmem_h = tmem_base + 2 * FCH;                 // 64 columns: 128 hidden values of a chunk, two per column
+  const uint32_t tmem_o = tmem_base + 2 * FCH + FCH / 2;       // O0 (, O1 = O0 + C)
 
   // Buffer bookkeeping shared by all roles.  Tile i of this CTA uses y buffer i % XBUF for the (i / XBUF)-th time and
-  // output accumulator i % OBUF for the (i / OBUF)-th time; chunk g uses S / H buffer g & 1 for the (g >> 1)-th time.
+  // output accumulator i % OBUF for the (i / OBUF)-th time; chunk g uses S buffer g & 1 for the (g >> 1)-th time and the
+  // single H buffer for the g-th time.
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop; one elected lane issues) =====================
     {
       int slot = 0;
       uint32_t rphase = 0;
-      TR_DECL
       auto issue_x = [&](int ti) {
         const int xb = ti % K::XBUF;
         const uint32_t use = (uint32_t)(ti / K::XBUF);
-        TR_BEGIN
         mbar_wait(smem_u32(x_empty + xb), (use & 1) ^ 1);
-        TR_END(0)
         const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
         if (elect_one()) {
           mbar_expect_tx(smem_u32(x_full + xb), K::X_BYTES);
@@ -186,57 +225,77 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         __syncwarp();
       };
       if (my_tiles > 0) issue_x(0);
+      if constexpr (K::RESIDENT) {
+        // both weight matrices, once: W1 chunk j = rows [128 j, 128 j + 128) in XKB K-blocks; W2 chunk j = columns
+        // [128 j, 128 j + 128) of all C rows in 4 K-blocks
+        if (my_tiles > 0 && elect_one()) {
+          mbar_expect_tx(smem_u32(w_full), K::W_BYTES);
 #pragma unroll 1
-      for (int g = 0; g < total + 2; ++g) {          // same order as the MMA warp: W1 of chunk g, then W2 of chunk g-2
-        if (g < total) {
-          const int ti = g / K::NCH, j = g - ti * K::NCH;
+          for (int j = 0; j < K::NCH; ++j) {
 #pragma unroll 1
-          for (int part = 0; part < K::P1; ++part) {
-            TR_BEGIN
-            mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
-            TR_END(1)
-            if (elect_one()) {
-              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
-#pragma unroll
-              for (int kb = 0; kb < K::KB1; ++kb)
-                tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
-                            (part * K::KB1 + kb) * FKB, j * FCH);
-            }
-            __syncwarp();
-            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
+            for (int kb = 0; kb < K::XKB; ++kb)
+              tma_load_2d(w_smem + j * K::W1_CHUNK + kb * FBLK, &tm_w1, smem_u32(w_full), kb * FKB, j * FCH);
+#pragma unroll 1
+            for (int kb = 0; kb < K::HKB; ++kb)
+              tma_load_2d(w_smem + K::NCH * K::W1_CHUNK + j * K::W2_CHUNK + kb * (C * 64), &tm_w2, smem_u32(w_full),
+                          j * FCH + kb * FKB, 0);
           }
-          // next tile's y block: a whole tile ahead with two buffers, else as soon as this tile's fc1s can retire
-          if (ti + 1 < my_tiles && j == (K::XBUF == 2 ? 0 : K::NCH - 1)) issue_x(ti + 1);
         }
-        if (g >= 2) {
-          const int gj = g - 2, jj = gj % K::NCH;
+        __syncwarp();
+        // y blocks a tile ahead (two buffers)
 #pragma unroll 1
-          for (int part = 0; part < K::P2; ++part) {
-            TR_BEGIN
-            mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
-            TR_END(1)
-            if (elect_one()) {
-              mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+        for (int ti = 1; ti < my_tiles; ++ti) issue_x(ti);
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < total + 2; ++g) {          // same order as the MMA warp: W1 of chunk g, then W2 of chunk g-2
+          if (g < total) {
+            const int ti = g / K::NCH, j = g - ti * K::NCH;
+#pragma unroll 1
+            for (int part = 0; part < K::P1; ++part) {
+              mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
 #pragma unroll
-              for (int kb = 0; kb < K::KB2; ++kb)
-                tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
-                            jj * FCH + (part * K::KB2 + kb) * FKB, 0);
+                for (int kb = 0; kb < K::KB1; ++kb)
+                  tma_load_2d(ring_smem + slot * K::SLOT + kb * FBLK, &tm_w1, smem_u32(ring_full + slot),
+                              (part * K::KB1 + kb) * FKB, j * FCH);
+              }
+              __syncwarp();
+              if (++slot == NRING) { slot = 0; rphase ^= 1; }
             }
-            __syncwarp();
-            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
+            // next tile's y block: as soon as this tile's fc1s can retire
+            if (ti + 1 < my_tiles && j == K::NCH - 1) issue_x(ti + 1);
+          }
+          if (g >= 2) {
+            const int gj = g - 2, jj = gj % K::NCH;
+#pragma unroll 1
+            for (int part = 0; part < K::P2; ++part) {
+              mbar_wait(smem_u32(ring_empty + slot), rphase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(smem_u32(ring_full + slot), K::SLOT);
+#pragma unroll
+                for (int kb = 0; kb < K::KB2; ++kb)
+                  tma_load_2d(ring_smem + slot * K::SLOT + kb * (C * 64), &tm_w2, smem_u32(ring_full + slot),
+                              jj * FCH + (part * K::KB2 + kb) * FKB, 0);
+              }
+              __syncwarp();
+              if (++slot == NRING) { slot = 0; rphase ^= 1; }
+            }
           }
         }
       }
-      TR_DUMP(0)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop; one elected lane issues) =====================
     {
       int slot = 0;
       uint32_t rphase = 0;
-      TR_DECL
       // descriptor bases: only the 14-bit start-address field changes between operands
-      const uint64_t dx0 = umma_desc_kmajor<64>(x_smem), dh0 = umma_desc_kmajor<64>(h_smem), dr0 = umma_desc_kmajor<64>(ring_smem);
+      const uint64_t dx0 = umma_desc_kmajor<64>(x_smem), dw0 = umma_desc_kmajor<64>(w_smem), dr0 = umma_desc_kmajor<64>(ring_smem);
+      if constexpr (K::RESIDENT) {
+        if (my_tiles > 0) mbar_wait(smem_u32(w_full), 0);
+        tc_fence_after();
+      }
       // fc1 runs two chunks ahead of fc2: S[g & 1] is free as soon as the epilogue has pulled chunk g-2 out of TMEM,
       // long before that chunk's GELU output is back in H -- so the next chunk's accumulator is always waiting for
       // the epilogue group instead of the other way round
@@ -245,98 +304,112 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         if (g < total) {
           const int ti = g / K::NCH, j = g - ti * K::NCH;
           const int xb = ti % K::XBUF;
-          if (j == 0) {
-            TR_BEGIN
-            mbar_wait(smem_u32(x_full + xb), (uint32_t)(ti / K::XBUF) & 1);
-            TR_END(0)
-          }
+          if (j == 0) mbar_wait(smem_u32(x_full + xb), (uint32_t)(ti / K::XBUF) & 1);
           const int b = g & 1;
-          TR_BEGIN
           mbar_wait(smem_u32(s_empty + b), ((uint32_t)(g >> 1) & 1) ^ 1);
-          TR_END(1)
           tc_fence_after();
           const uint32_t d = tmem_base + b * FCH;
-#pragma unroll 1
-          for (int part = 0; part < K::P1; ++part) {
-            TR_BEGIN
-            mbar_wait(smem_u32(ring_full + slot), rphase);
-            TR_END(2)
-            tc_fence_after();
-            const uint64_t da = dx0 + (uint64_t)((xb * K::X_BYTES + part * K::KB1 * FBLK) >> 4);
-            const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+          if constexpr (K::RESIDENT) {
+            const uint64_t da = dx0 + (uint64_t)((xb * K::X_BYTES) >> 4);
+            const uint64_t dw = dw0 + (uint64_t)((j * K::W1_CHUNK) >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int kb = 0; kb < K::KB1; ++kb)
+              for (int kb = 0; kb < K::XKB; ++kb)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1,
-                         (part | kb | k) ? 1u : 0u);
-              tc_commit(smem_u32(ring_empty + slot));
-              if (part == K::P1 - 1) {
-                tc_commit(smem_u32(s_full + b));
-                if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));      // y buffer may be refilled
-              }
+                  tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1, (kb | k) ? 1u : 0u);
+              tc_commit(smem_u32(s_full + b));
+              if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));        // y buffer may be refilled
             }
             __syncwarp();
-            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
+          } else {
+#pragma unroll 1
+            for (int part = 0; part < K::P1; ++part) {
+              mbar_wait(smem_u32(ring_full + slot), rphase);
+              tc_fence_after();
+              const uint64_t da = dx0 + (uint64_t)((xb * K::X_BYTES + part * K::KB1 * FBLK) >> 4);
+              const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < K::KB1; ++kb)
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    tc_mma(d, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * FBLK + k * 32) >> 4), p.idesc1,
+                           (part | kb | k) ? 1u : 0u);
+                tc_commit(smem_u32(ring_empty + slot));
+                if (part == K::P1 - 1) {
+                  tc_commit(smem_u32(s_full + b));
+                  if (j == K::NCH - 1) tc_commit(smem_u32(x_empty + xb));      // y buffer may be refilled
+                }
+              }
+              __syncwarp();
+              if (++slot == NRING) { slot = 0; rphase ^= 1; }
+            }
           }
         }
         if (g >= 2) {
           const int gj = g - 2, ti = gj / K::NCH, jj = gj - ti * K::NCH;
-          const int hb = gj & 1, ob = ti % K::OBUF;
-          TR_BEGIN
-          mbar_wait(smem_u32(h_full + hb), (uint32_t)(gj >> 1) & 1);
-          TR_END(3)
+          const int ob = ti % K::OBUF;
+          mbar_wait(smem_u32(h_full), (uint32_t)gj & 1);
           tc_fence_after();
           if (jj == 0) {
-            TR_BEGIN
             mbar_wait(smem_u32(o_empty + ob), ((uint32_t)(ti / K::OBUF) & 1) ^ 1);
-            TR_END(4)
             tc_fence_after();
           }
           const uint32_t dout = tmem_o + ob * C;
-#pragma unroll 1
-          for (int part = 0; part < K::P2; ++part) {
-            TR_BEGIN
-            mbar_wait(smem_u32(ring_full + slot), rphase);
-            TR_END(5)
-            tc_fence_after();
-            const uint64_t da = dh0 + (uint64_t)((hb * K::H_BYTES + part * K::KB2 * FBLK) >> 4);
-            const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+          // A = H from tensor memory: K slice k (16 hidden values) = 8 columns
+          if constexpr (K::RESIDENT) {
+            const uint64_t dw = dw0 + (uint64_t)((K::NCH * K::W1_CHUNK + jj * K::W2_CHUNK) >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int kb = 0; kb < K::KB2; ++kb)
+              for (int kb = 0; kb < K::HKB; ++kb)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  tc_mma(dout, da + ((kb * FBLK + k * 32) >> 4), dw + ((kb * C * 64 + k * 32) >> 4), p.idesc2,
-                         (jj | part | kb | k) ? 1u : 0u);
-              tc_commit(smem_u32(ring_empty + slot));
-              if (part == K::P2 - 1) {
-                tc_commit(smem_u32(h_empty + hb));
-                if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
-              }
+                  tc_mma_ts(dout, tmem_h + (uint32_t)((kb * 2 + k) * 8), dw + ((kb * C * 64 + k * 32) >> 4), p.idesc2,
+                            (jj | kb | k) ? 1u : 0u);
+              tc_commit(smem_u32(h_empty + (gj & 1)));
+              if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
             }
             __syncwarp();
-            if (++slot == K::RING) { slot = 0; rphase ^= 1; }
+          } else {
+#pragma unroll 1
+            for (int part = 0; part < K::P2; ++part) {
+              mbar_wait(smem_u32(ring_full + slot), rphase);
+              tc_fence_after();
+              const uint64_t dw = dr0 + (uint64_t)((slot * K::SLOT) >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int kb = 0; kb < K::KB2; ++kb)
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    tc_mma_ts(dout, tmem_h + (uint32_t)(((part * K::KB2 + kb) * 2 + k) * 8), dw + ((kb * C * 64 + k * 32) >> 4),
+                              p.idesc2, (jj | part | kb | k) ? 1u : 0u);
+                tc_commit(smem_u32(ring_empty + slot));
+                if (part == K::P2 - 1) {
+                  tc_commit(smem_u32(h_empty + (gj & 1)));
+                  if (jj == K::NCH - 1) tc_commit(smem_u32(o_full + ob));
+                }
+              }
+              __syncwarp();
+              if (++slot == NRING) { slot = 0; rphase ^= 1; }
+            }
           }
         }
       }
-      TR_DUMP(8)
     }
   } else {
     // ===================== epilogue =====================
-    // The 16 warps form two groups of 8; group g owns the chunks with (chunk index & 1) == g, i.e. TMEM buffer S[g] and
-    // smem buffer H[g].  While one group sits in a TMEM-load / barrier / smem-fence latency the other one issues math.
+    // The 16 warps form two groups of 8; group g owns the chunks with (chunk index & 1) == g, i.e. TMEM buffer S[g].
+    // While one group sits in a TMEM-load / barrier latency the other one issues math.
     const int q = warp & 3;                  // TMEM lane quarter = rows 32q .. 32q+31 of the tile
     const int grp = (warp - 2) >> 3;
     const int half = ((warp - 2) >> 2) & 1;  // which 64 hidden columns (2 K-blocks) of the group's chunk
     const int s = (warp - 2) >> 2;           // column-chunk phase of the O epilogue
     const int row = q * 32 + lane;
-    const int sw = (row >> 1) & 3;           // 64B-swizzle XOR for this row
-    // output staging tile of this warp (dedicated: the drain of tile t overlaps H traffic of tile t+1)
-    uint8_t* my_stage = stage_gen + (warp - 2) * (32 * 64);
+    // output staging tile of this warp (dedicated: the drain of tile t overlaps the next tile's chunks); only the warps
+    // that own output columns (s < C / 32) have one
+    uint8_t* my_stage = stage_gen + (s * 4 + q) * (32 * 64);
     T* xg = reinterpret_cast<T*>(p.x);
-    TR_DECL
     // this warp's share of tile ti's output accumulator: + b2, * gamma, + residual, staged coalesced store (in place)
     auto drain_output = [&](int ti) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -354,9 +427,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           res[ci][gq] = make_uint4(0, 0, 0, 0);
           if (c < C / 32 && m < p.M) res[ci][gq] = *reinterpret_cast<const uint4*>(xg + m * C + c * 32 + gq * 8);
         }
-      TR_BEGIN
       mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
-      TR_END(2)
       tc_fence_after();
       if (s >= C / 32) {
         tc_fence_before();
@@ -430,6 +501,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     for (int g = grp; g < total; g += 2) {
       const int ti = g / K::NCH, j = g - ti * K::NCH;
       const int b = grp;
+      if constexpr (K::OBUF == 1) {
+        // One output accumulator and one H buffer: fc2 of the next tile's first chunk waits for EVERY warp's drain of this
+        // tile, and the chunk after it (owned by the group that had the tile's LAST chunk) waits (h_empty) for that fc2 --
+        // a circular wait if that group drained one chunk late like the other one does.  It drains first instead; its
+        // accumulator wait is short (the tile's last fc2 was issued as soon as this group stored its H).
+        if (pending >= 0 && grp == ((K::NCH - 1) & 1)) { drain_output(pending); pending = -1; }
+      }
       if constexpr (LN) {
         if (ti != ln_ti) {
           if (ln_ti < 0) {
@@ -444,9 +522,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         }
       }
       const uint32_t n_use = (uint32_t)(g >> 1);
-      TR_BEGIN
       mbar_wait(smem_u32(s_full + b), n_use & 1);
-      TR_END(0)
       tc_fence_after();
 #pragma unroll 1
       for (int hk = 0; hk < 2; ++hk) {
@@ -479,16 +555,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
                                         *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
           }
         }
-        TR_BEGIN
-        if (hk == 0) mbar_wait(smem_u32(h_empty + b), (n_use & 1) ^ 1);   // fc2 that last read this buffer retired
-        TR_END(1)
-        uint8_t* hrow = h_gen + b * K::H_BYTES + kb * FBLK + row * 64;
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(hrow + ((gq ^ sw) << 4)) = pk[gq];
+        if (hk == 0) {                       // the single H buffer: fc2 of the previous chunk (g - 1) has retired;
+          // that is completion number (g - 1) / 2 of barrier (g - 1) & 1 (g = 0: parity 1 of a fresh barrier passes)
+          mbar_wait(smem_u32(h_empty + ((g - 1) & 1)), (uint32_t)((g - 1) >> 1) & 1u);
+          tc_fence_after();
+        }
+        // 32 hidden values of this thread's row = 16 packed columns of H
+        tc_st16(tmem_h + ((uint32_t)(q * 32) << 16) + (uint32_t)(kb * 16), pk[0], pk[1], pk[2], pk[3]);
       }
-      fence_async_smem();                                          // generic-proxy writes -> visible to the tensor core
+      tc_wait_st();
+      tc_fence_before();                                           // TMEM writes ordered before the MMA warp's reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(h_full + b));
+      if (lane == 0) mbar_arrive(smem_u32(h_full));
 
       // The tile's output accumulator is complete only after the OTHER group's last chunk went through fc2, so this
       // warp drains tile ti one chunk late (after its first chunk of the next tile) instead of idling on o_full.
@@ -507,8 +585,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       }
     }
     if (pending >= 0) drain_output(pending);
-    if (lane == 0 && warp == 2) { TR_DUMP(16) }
-    if (lane == 0 && warp == 10) { TR_DUMP(24) }
   }
 
   tc_fence_before();
@@ -609,6 +685,8 @@ int mlp_fused(int dtype, const void* y, const float* ln_stats, float ln_eps, con
   p.M = M;
   p.tiles = (int)((M + FM - 1) / FM);
   p.idesc1 = umma_idesc_f16(dtype == GCV_BF16, FM, FCH);
+  // (measured: kind::f16 with an fp16 A operand in tensor memory and a bf16 B operand is an illegal instruction on
+  // sm_100a -- H has to be converted to the model's 16-bit type)
   p.idesc2 = umma_idesc_f16(dtype == GCV_BF16, FM, C);
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.x = x;
   p.ln_stats = ln_stats; p.colsum1 = colsum1; p.ln_eps = ln_eps;

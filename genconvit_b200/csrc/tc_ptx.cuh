@@ -18,14 +18,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: a warp whose phase is not complete sleeps in hardware (NANOSLEEP.SYNCS, woken by
+// the barrier) instead of spinning through the loop below -- spinning waiters were ~13 % of the fused MLP's issue slots
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
   return ok != 0;
 }
@@ -177,5 +179,4 @@ __host__ __device__ inline uint32_t umma_idesc_f16(bool bf16, int m, int n) {
   const uint32_t fmt = bf16 ? 1u : 0u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-
 }  // namespace gcv
