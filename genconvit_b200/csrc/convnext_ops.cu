@@ -47,7 +47,9 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 dwconv7_ln_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ taps,
                   const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                  float eps, int H, int W, int C, int tiles_w, int tiles_h) {
+                  float eps, int H, int W, int C, int tiles_w, int tiles_h, int fuse_ln) {
+  // fuse_ln = 0 (channel counts whose [32 pixels][C] fp32 tile does not fit in shared memory, i.e. convnext_large's
+  // C = 1536 in the fp32 mode): conv + bias go straight to y, the caller runs layernorm_rows over y afterwards
   extern __shared__ __align__(16) uint8_t smem[];
   T* halo = reinterpret_cast<T*>(smem);                                     // [DW_HH][DW_HW][DW_CK]
   float* outs = reinterpret_cast<float*>(smem + DW_HH * DW_HW * DW_CK * sizeof(T));  // [32][C]
@@ -112,12 +114,24 @@ dwconv7_ln_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
           }
         }
       }
+      if (fuse_ln) {
 #pragma unroll
-      for (int i = 0; i < DW_TW; ++i)
-        *reinterpret_cast<float2*>(outs + (r * DW_TW + i) * C + c) = make_float2(acc0[i], acc1[i]);
+        for (int i = 0; i < DW_TW; ++i)
+          *reinterpret_cast<float2*>(outs + (r * DW_TW + i) * C + c) = make_float2(acc0[i], acc1[i]);
+      } else if (h0 + r < H) {
+#pragma unroll
+        for (int i = 0; i < DW_TW; ++i) {
+          if (w0 + i < W) {
+            T* dst = y + (((int64_t)b * H + h0 + r) * W + w0 + i) * C + c;
+            if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(dst) = make_float2(acc0[i], acc1[i]);
+            else *reinterpret_cast<uint32_t*>(dst) = pack2<T>(acc0[i], acc1[i]);
+          }
+        }
+      }
     }
     __syncthreads();
   }
+  if (!fuse_ln) return;
 
   // ---- LayerNorm: warp w normalises the 8 pixels of tile row w ----
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -781,15 +795,19 @@ int dwconv7_ln(int dtype, const void* x, void* y, const float* taps, const float
   GCV_REQUIRE(grid < 2147483647LL, "dwconv7_ln: grid too large");
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
-    const size_t smem = DW_HH * DW_HW * DW_CK * sizeof(T) + (size_t)DW_TH * DW_TW * C * sizeof(float);
+    const size_t halo_bytes = DW_HH * DW_HW * DW_CK * sizeof(T);
+    size_t smem = halo_bytes + (size_t)DW_TH * DW_TW * C * sizeof(float);
+    const int fuse_ln = smem <= 200 * 1024 ? 1 : 0;
+    if (!fuse_ln) smem = halo_bytes;
     static unsigned long long attr_devs = 0;
     if (first_on_device(attr_devs)) {
       cudaFuncSetAttribute(dwconv7_ln_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    GCV_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C=%d needs %zu B of shared memory", C, smem);
     dwconv7_ln_kernel<T><<<(unsigned)grid, 128, smem, stream>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y),
-                                                               taps, bias, ln_w, ln_b, eps, H, W, C, tiles_w, tiles_h);
-    return check_launch("dwconv7_ln");
+                                                               taps, bias, ln_w, ln_b, eps, H, W, C, tiles_w, tiles_h, fuse_ln);
+    const int rc = check_launch("dwconv7_ln");
+    if (rc != GCV_OK || fuse_ln) return rc;
+    return layernorm_rows(dtype, y, y, ln_w, ln_b, eps, (int64_t)B * H * W, C, stream);
   });
 }
 
@@ -824,9 +842,15 @@ int stem_patchify(int dtype, bool nchw, const void* x, void* a, int B, int H, in
 
 int layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps, int64_t rows, int C,
                    cudaStream_t stream) {
-  GCV_REQUIRE(C % 8 == 0 && C <= 2048 && rows > 0, "layernorm_rows: unsupported C=%d", C);
+  GCV_REQUIRE(C % 8 == 0 && C <= 3072 && rows > 0, "layernorm_rows: unsupported C=%d", C);
   return dispatch(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
+    if (C > 2048) {                         // swin_large patch merging: LayerNorm(4 * 768)
+      constexpr int LPR = 32, ITER = 12, RPB = 256 / LPR;
+      layernorm_rows_kernel<T, LPR, ITER><<<(unsigned)((rows + RPB - 1) / RPB), 256, 0, stream>>>(
+          reinterpret_cast<const T*>(x), reinterpret_cast<T*>(y), w, b, eps, rows, C);
+      return check_launch("layernorm_rows");
+    }
     return ln_dispatch(C, [&](auto lpr, auto iter) -> int {
       constexpr int LPR = decltype(lpr)::value, ITER = decltype(iter)::value, RPB = 256 / LPR;
       layernorm_rows_kernel<T, LPR, ITER><<<(unsigned)((rows + RPB - 1) / RPB), 256, 0, stream>>>(

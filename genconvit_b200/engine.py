@@ -61,6 +61,10 @@ class PackedConvNeXt:
 
     def __init__(self, sd, dev, dt):
         self.dev, self.dt = dev, dt
+        # variant (convnext_tiny / convnext_large, reference prediction.py:314-318) read off the state_dict itself
+        DIMS = tuple(sd[f"stages.{s}.blocks.0.gamma"].shape[0] for s in range(4))
+        DEPTHS = tuple(sum(1 for k in sd if k.startswith(f"stages.{s}.blocks.") and k.endswith(".gamma")) for s in range(4))
+        self.dims, self.depths = DIMS, DEPTHS
         w = sd["stem.0.weight"]                                   # [96,3,4,4] -> [96, (kh,kw,c)]
         self.stem_w = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], 48), dev, dt)
         self.stem_w_oihw = _cd(w.reshape(w.shape[0], 48), dev, dt)  # [96, (c,kh,kw)]: the fused stem reads NCHW frames
@@ -113,6 +117,7 @@ class PackedConvNeXt:
         genconvit_ed.py:82-83 / genconvit_vae.py:111-112.
         """
         dev, dt = self.dev, self.dt
+        DIMS = self.dims
         if isinstance(a0, list):
             # 16-bit modes: a0 is a list of frame sources (tensor, nchw?, n_images, H, W), one per run of tokens; the
             # fused stem kernel turns each straight into normalised tokens (no im2col matrix, no separate LayerNorm)
@@ -146,7 +151,9 @@ class PackedConvNeXt:
                 segs, m = new, m2
             y = _empty((m, c), dt, dev)
             fused = FUSED_MLP and backend == L.GEMM_AUTO and L.mlp_fused_supported(dt, c)
-            fold = LN_FOLD and backend == L.GEMM_AUTO and dt != torch.float32
+            # the folded-LayerNorm GEMM epilogue stages its per-column vectors in shared memory (N <= 3072: C <= 768)
+            fold = LN_FOLD and backend == L.GEMM_AUTO and dt != torch.float32 and (4 * c <= 3072 or
+                                                                                    L.mlp_fused_supported(dt, c))
             stats = _empty((m, c // 32, 2), torch.float32, dev) if fold else None
             hid = None if fused else _empty((m, 4 * c), dt, dev)
             rowstat = _empty((m, 2), torch.float32, dev) if (fold and not fused) else None
@@ -189,7 +196,7 @@ class PackedConvNeXt:
     def forward_images(self, x, act=L.ACT_NONE, backend=L.GEMM_AUTO):
         """``backbone(x)`` for fp32 NCHW frames -> fp32 [N,1000] ImageNet logits."""
         n, _, hh, ww = x.shape
-        if FUSED_STEM and self.dt != torch.float32 and backend == L.GEMM_AUTO:
+        if FUSED_STEM and self.dt != torch.float32 and backend == L.GEMM_AUTO and self.dims[0] == 96:
             a0 = [(x, True, n, hh, ww)]
         else:
             a0 = _empty((n * (hh // 4) * (ww // 4), 48), self.dt, self.dev)
@@ -199,7 +206,7 @@ class PackedConvNeXt:
         return out
 
 
-SWIN_DEPTHS = (2, 2, 6, 2)
+SWIN_DEPTHS = (2, 2, 6, 2)           # swin_tiny_patch4_window7_224; the large variant is read off the state_dict
 SWIN_HEADS = (3, 6, 12, 24)
 
 
@@ -212,6 +219,10 @@ class PackedSwin:
 
     def __init__(self, sd, dev, dt):
         self.dev, self.dt = dev, dt
+        self.embed = sd["patch_embed.proj.weight"].shape[0]
+        SWIN_DEPTHS = tuple(sum(1 for k in sd if k.startswith(f"layers.{l}.blocks.") and k.endswith(".norm1.weight"))
+                            for l in range(4))
+        self.heads = tuple(sd[f"layers.{l}.blocks.0.attn.relative_position_bias_table"].shape[1] for l in range(4))
         w = sd["patch_embed.proj.weight"]                         # [96,3,4,4] -> [96, (kh,kw,c)]
         self.pe_w = _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], 48), dev, dt)
         self.pe_b = _f32(sd["patch_embed.proj.bias"], dev)
@@ -244,8 +255,8 @@ class PackedSwin:
         dev, dt = self.dev, self.dt
         n, _, hh, ww = x.shape
         if (hh, ww) != (224, 224):
-            raise L.GcvError(f"swin_tiny_patch4_window7_224 takes 224x224 frames, got {hh}x{ww}")
-        res, c = 56, 96
+            raise L.GcvError(f"swin_*_patch4_window7_224 takes 224x224 frames, got {hh}x{ww}")
+        res, c = 56, self.embed
         m = n * res * res
         a0 = _empty((m, 48), dt, dev)
         L.stem_patchify_nchw(x, a0, n, hh, ww)
@@ -253,7 +264,7 @@ class PackedSwin:
         L.gemm(a0, self.pe_w, t, m, c, 48, bias=self.pe_b, backend=backend)
         L.layernorm_rows(t, t, self.pe_ln[0], self.pe_ln[1], 1e-5, m, c)
         for l, layer in enumerate(self.layers):
-            heads = SWIN_HEADS[l]
+            heads = self.heads[l]
             h = _empty((m, c), dt, dev)
             qkv = _empty((m, 3 * c), dt, dev)
             att = _empty((m, c), dt, dev)
@@ -387,7 +398,7 @@ class PackedED:
         dec, dh, dw = self.decode(e, n, h, w, backend)
         assert (dh, dw) == (hh, ww)
         th, tw = hh // 4, ww // 4
-        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO:
+        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO and self.backbone.dims[0] == 96:
             a0 = [(dec, False, n, hh, ww), (x, True, n, hh, ww)]
         else:
             a0 = _empty((2 * n * th * tw, 48), dt, dev)
@@ -505,7 +516,7 @@ class PackedVAE:
         t1 = (hh // 4, ww // 4)
         t2 = (h2 // 4, w2 // 4)
         m1 = n * t1[0] * t1[1]
-        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO:
+        if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO and self.backbone.dims[0] == 96:
             a0 = [(x, True, n, hh, ww), (xhat, False, n, h2, w2)]
         else:
             a0 = _empty((m1 + n * t2[0] * t2[1], 48), dt, dev)

@@ -15,8 +15,14 @@ import torch.nn as nn
 from . import engine
 from . import lib as L
 
-DEPTHS = engine.DEPTHS
+DEPTHS = engine.DEPTHS            # convnext_tiny (the reference's default, model/config.yaml:2)
 DIMS = engine.DIMS
+# timm model name -> (dims, depths) / (embed, depths, heads): the tiny defaults and the '--s large' variants of
+# reference prediction.py:314-318
+CONVNEXT_VARIANTS = {"convnext_tiny": ((96, 192, 384, 768), (3, 3, 9, 3)),
+                     "convnext_large": ((192, 384, 768, 1536), (3, 3, 27, 3))}
+SWIN_VARIANTS = {"swin_tiny_patch4_window7_224": (96, (2, 2, 6, 2), (3, 6, 12, 24)),
+                 "swin_large_patch4_window7_224": (192, (2, 2, 18, 2), (6, 12, 24, 48))}
 
 
 def weights_fingerprint(module):
@@ -79,8 +85,10 @@ class ConvNeXt(nn.Module):
     """convnext_tiny: forward = head(norm_pre(stages(stem(x)))).  A ``patch_embed`` attribute
     attached by the caller (reference genconvit_ed.py:70) is carried in the state_dict and never read."""
 
-    def __init__(self):
+    def __init__(self, dims=DIMS, depths=DEPTHS):
         super().__init__()
+        DIMS, DEPTHS = tuple(dims), tuple(depths)
+        self.dims, self.depths = DIMS, DEPTHS
         self.stem = nn.Sequential(nn.Conv2d(3, DIMS[0], 4, stride=4), nn.LayerNorm(DIMS[0], eps=1e-6))
         stages, cin = [], DIMS[0]
         for c, d in zip(DIMS, DEPTHS):
@@ -172,10 +180,10 @@ class _SwinLayer(nn.Module):
 
 
 class _PatchEmbed(nn.Module):
-    def __init__(self):
+    def __init__(self, embed=96):
         super().__init__()
-        self.proj = nn.Conv2d(3, 96, 4, stride=4)
-        self.norm = nn.LayerNorm(96)
+        self.proj = nn.Conv2d(3, embed, 4, stride=4)
+        self.norm = nn.LayerNorm(embed)
 
 
 class SwinTransformer(nn.Module):
@@ -189,18 +197,19 @@ class SwinTransformer(nn.Module):
     recompute both from (window, shift, resolution), which is what defines them.
     """
 
-    def __init__(self):
+    def __init__(self, embed=96, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24)):
         super().__init__()
-        self.patch_embed = _PatchEmbed()
+        self.embed, self.depths, self.heads = embed, tuple(depths), tuple(heads)
+        self.patch_embed = _PatchEmbed(embed)
         layers, res = [], 56
-        for l, (d, h) in enumerate(zip((2, 2, 6, 2), (3, 6, 12, 24))):
-            layers.append(_SwinLayer(96 * 2 ** l, d, h, res, downsample=l < 3))
+        for l, (d, h) in enumerate(zip(depths, heads)):
+            layers.append(_SwinLayer(embed * 2 ** l, d, h, res, downsample=l < 3))
             if l < 3:
                 res //= 2
         self.layers = nn.Sequential(*layers)
-        self.norm = nn.LayerNorm(768)
-        self.head = nn.Linear(768, 1000)
-        self.num_features = 768
+        self.norm = nn.LayerNorm(8 * embed)
+        self.head = nn.Linear(8 * embed, 1000)
+        self.num_features = 8 * embed
         self._packed = None
         self.compute_dtype = None
 
@@ -222,15 +231,15 @@ class SwinTransformer(nn.Module):
         return self._packed.forward_images(x.float().contiguous())
 
 
-_MODELS = {"convnext_tiny": ConvNeXt, "swin_tiny_patch4_window7_224": SwinTransformer}
-
-
 def create_model(name, pretrained=False, num_classes=1000, drop_path_rate=0.0, head_init_scale=1.0, **_):
-    """Drop-in for the two ``timm.create_model`` calls of the reference; never downloads weights."""
-    if name not in _MODELS:
-        raise NotImplementedError(
-            f"backbone {name!r}: only convnext_tiny / swin_tiny_patch4_window7_224 are built "
-            "(the '--s large' variants of reference prediction.py:314-318 are SURVEY.md section 8f rank 4)")
+    """Drop-in for the two ``timm.create_model`` calls of the reference; never downloads weights.  Builds the models the
+    reference can select: the tiny defaults (model/config.yaml:2-3) and the ``--s large`` pair (prediction.py:314-318)."""
     if num_classes != 1000:
         raise NotImplementedError("only the 1000-class heads the reference uses are supported")
-    return _MODELS[name]()
+    if name in CONVNEXT_VARIANTS:
+        return ConvNeXt(*CONVNEXT_VARIANTS[name])
+    if name in SWIN_VARIANTS:
+        return SwinTransformer(*SWIN_VARIANTS[name])
+    raise NotImplementedError(
+        f"backbone {name!r}: the reference only ever selects convnext_{{tiny,large}} / "
+        "swin_{tiny,large}_patch4_window7_224 (model/config.yaml:2-3, prediction.py:314-318)")

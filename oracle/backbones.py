@@ -19,6 +19,29 @@ import torch.nn.functional as F
 CONVNEXT_TINY = dict(depths=(3, 3, 9, 3), dims=(96, 192, 384, 768))
 SWIN_TINY = dict(depths=(2, 2, 6, 2), heads=(3, 6, 12, 24), embed=96, window=7,
                  patch=4, img=224)
+# the "--s large" variants of reference prediction.py:314-318 (timm convnext_large / swin_large_patch4_window7_224)
+CONVNEXT_LARGE = dict(depths=(3, 3, 27, 3), dims=(192, 384, 768, 1536))
+SWIN_LARGE = dict(depths=(2, 2, 18, 2), heads=(6, 12, 24, 48), embed=192, window=7,
+                  patch=4, img=224)
+CONVNEXT = {"convnext_tiny": CONVNEXT_TINY, "convnext_large": CONVNEXT_LARGE}
+SWIN = {"swin_tiny_patch4_window7_224": SWIN_TINY, "swin_large_patch4_window7_224": SWIN_LARGE}
+
+
+def convnext_cfg_of(sd, p=""):
+    """Variant (tiny / large) of the ConvNeXt stored under prefix ``p``, read off the stem width."""
+    c0 = sd[p + "stem.0.weight"].shape[0]
+    for cfg in CONVNEXT.values():
+        if cfg["dims"][0] == c0:
+            return cfg
+    raise ValueError(f"no ConvNeXt variant with stem width {c0}")
+
+
+def swin_cfg_of(sd, p=""):
+    e = sd[p + "patch_embed.proj.weight"].shape[0]
+    for cfg in SWIN.values():
+        if cfg["embed"] == e:
+            return cfg
+    raise ValueError(f"no Swin variant with embedding width {e}")
 
 
 # --------------------------------------------------------------------------
@@ -48,7 +71,7 @@ def convnext_features(sd, p, x, taps=None):
     x = _ln2d(x, sd[p + "stem.1.weight"], sd[p + "stem.1.bias"], 1e-6)
     if taps is not None:
         taps["stem"] = x
-    for s, depth in enumerate(CONVNEXT_TINY["depths"]):
+    for s, depth in enumerate(convnext_cfg_of(sd, p)["depths"]):
         q = f"{p}stages.{s}."
         if s > 0:
             x = _ln2d(x, sd[q + "downsample.0.weight"], sd[q + "downsample.0.bias"], 1e-6)
@@ -158,8 +181,8 @@ def swin_patch_merging(sd, p, x, res):
 
 
 def swin_forward(sd, p, x):
-    """swin_tiny_patch4_window7_224 classifier: [N,3,224,224] -> [N,1000]."""
-    cfg = SWIN_TINY
+    """swin_{tiny,large}_patch4_window7_224 classifier: [N,3,224,224] -> [N,1000]."""
+    cfg = swin_cfg_of(sd, p)
     ws = cfg["window"]
     x = F.conv2d(x, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=cfg["patch"])
     x = x.flatten(2).transpose(1, 2)

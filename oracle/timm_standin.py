@@ -37,12 +37,13 @@ class _Shell(nn.Module):
 
 
 class _Net(_Shell):
-    _spec = staticmethod(lambda p: [])
+    _spec = staticmethod(lambda p, cfg: [])
     _fwd = None
+    _cfg = None
 
     def __init__(self):
         super().__init__()
-        for name, shape, kind in self._spec(""):
+        for name, shape, kind in self._spec("", self._cfg):
             t = make_tensor(name, shape, kind, seed=12345)
             self.put(name, t, buffer=kind == "rpi" or kind.startswith("attn_mask"))
 
@@ -56,22 +57,34 @@ class ConvNeXt(_Net):
     _spec = staticmethod(_convnext_spec)
     _fwd = staticmethod(backbones.convnext_forward)
 
+    _cfg = backbones.CONVNEXT_TINY
+
     def __init__(self):
         super().__init__()
         self.head.fc.out_features = 1000   # read at reference genconvit_ed.py:72 / genconvit_vae.py:99
-        self.num_features = 768
+        self.num_features = self._cfg["dims"][3]
 
 
 class SwinTransformer(_Net):
     _spec = staticmethod(_swin_spec)
     _fwd = staticmethod(backbones.swin_forward)
+    _cfg = backbones.SWIN_TINY
 
     def __init__(self):
         super().__init__()
-        self.num_features = 768
+        self.num_features = self._cfg["embed"] * 8
 
 
-_MODELS = {"convnext_tiny": ConvNeXt, "swin_tiny_patch4_window7_224": SwinTransformer}
+class ConvNeXtLarge(ConvNeXt):
+    _cfg = backbones.CONVNEXT_LARGE
+
+
+class SwinLarge(SwinTransformer):
+    _cfg = backbones.SWIN_LARGE
+
+
+_MODELS = {"convnext_tiny": ConvNeXt, "swin_tiny_patch4_window7_224": SwinTransformer,
+           "convnext_large": ConvNeXtLarge, "swin_large_patch4_window7_224": SwinLarge}
 
 
 def create_model(name, pretrained=False, num_classes=1000, drop_path_rate=0.0, head_init_scale=1.0, **kw):

@@ -19,17 +19,17 @@ from collections import OrderedDict
 
 import torch
 
-from .backbones import CONVNEXT_TINY, SWIN_TINY, swin_attn_mask, swin_relative_position_index
+from .backbones import CONVNEXT, CONVNEXT_TINY, SWIN, SWIN_TINY, swin_attn_mask, swin_relative_position_index
 
 LATENT = 12544          # reference model/config.yaml:4
 ENC_FLAT = 128 * 14 * 14  # reference model/genconvit_vae.py:34-37
 
 
-def _convnext_spec(p):
-    d = CONVNEXT_TINY["dims"]
+def _convnext_spec(p, cfg=CONVNEXT_TINY):
+    d = cfg["dims"]
     out = [(p + "stem.0.weight", (d[0], 3, 4, 4), "w"), (p + "stem.0.bias", (d[0],), "b"),
            (p + "stem.1.weight", (d[0],), "ln_w"), (p + "stem.1.bias", (d[0],), "b")]
-    for s, depth in enumerate(CONVNEXT_TINY["depths"]):
+    for s, depth in enumerate(cfg["depths"]):
         q, c = f"{p}stages.{s}.", d[s]
         if s > 0:
             out += [(q + "downsample.0.weight", (d[s - 1],), "ln_w"), (q + "downsample.0.bias", (d[s - 1],), "b"),
@@ -46,8 +46,7 @@ def _convnext_spec(p):
     return out
 
 
-def _swin_spec(p):
-    cfg = SWIN_TINY
+def _swin_spec(p, cfg=SWIN_TINY):
     ws, e = cfg["window"], cfg["embed"]
     out = [(p + "patch_embed.proj.weight", (e, 3, 4, 4), "w"), (p + "patch_embed.proj.bias", (e,), "b"),
            (p + "patch_embed.norm.weight", (e,), "ln_w"), (p + "patch_embed.norm.bias", (e,), "b")]
@@ -78,29 +77,36 @@ def _swin_spec(p):
     return out
 
 
-def _hybrid_spec(backbone_prefix):
+def _hybrid_spec(backbone_prefix, swin_cfg=SWIN_TINY):
     """HybridEmbed attached as <backbone>.patch_embed (reference model_embedder.py:16-37):
     proj = Conv2d(1000, 768, 1) because the probe output of the Swin classifier is [1,1000]."""
     p = backbone_prefix + "patch_embed."
     return ([(p + "proj.weight", (768, 1000, 1, 1), "w"), (p + "proj.bias", (768,), "b")]
-            + [(n, s, "alias:" + n.replace(p + "backbone.", "embedder.", 1)) for n, s, _ in _swin_spec(p + "backbone.")])
+            + [(n, s, "alias:" + n.replace(p + "backbone.", "embedder.", 1)) for n, s, _ in _swin_spec(p + "backbone.", swin_cfg)])
 
 
-def ed_spec():
+def _variant(size):
+    """'tiny' | 'large' -> (ConvNeXt cfg, Swin cfg), reference prediction.py:314-318."""
+    return CONVNEXT[f"convnext_{size}"], SWIN[f"swin_{size}_patch4_window7_224"]
+
+
+def ed_spec(size="tiny"):
     """reference model/genconvit_ed.py: Encoder 13-33, Decoder 43-58, GenConViTED 66-75."""
+    cn, sw = _variant(size)
     out = []
     for i, (ci, co) in zip((0, 3, 6, 9, 12), ((3, 16), (16, 32), (32, 64), (64, 128), (128, 256))):
         out += [(f"encoder.features.{i}.weight", (co, ci, 3, 3), "w_relu"), (f"encoder.features.{i}.bias", (co,), "b")]
     for i, (ci, co) in zip((0, 2, 4, 6, 8), ((256, 128), (128, 64), (64, 32), (32, 16), (16, 3))):
         out += [(f"decoder.features.{i}.weight", (ci, co, 2, 2), "w_convt"), (f"decoder.features.{i}.bias", (co,), "b")]
-    out += _convnext_spec("backbone.") + _hybrid_spec("backbone.") + _swin_spec("embedder.")
+    out += _convnext_spec("backbone.", cn) + _hybrid_spec("backbone.", sw) + _swin_spec("embedder.", sw)
     out += [("fc.weight", (500, 2000), "w_head1"), ("fc.bias", (500,), "b"),
             ("fc2.weight", (2, 500), "w_head2"), ("fc2.bias", (2,), "b_head2")]
     return out
 
 
-def vae_spec(latent=LATENT):
+def vae_spec(latent=LATENT, size="tiny"):
     """reference model/genconvit_vae.py: Encoder 15-37, Decoder 67-83, GenConViTVAE 93-105."""
+    cn, sw = _variant(size)
     out = []
     for i, (ci, co) in zip((0, 3, 6, 9), ((3, 16), (16, 32), (32, 64), (64, 128))):
         out += [(f"encoder.features.{i}.weight", (co, ci, 3, 3), "w_relu"), (f"encoder.features.{i}.bias", (co,), "b"),
@@ -114,7 +120,7 @@ def vae_spec(latent=LATENT):
             ("encoder.var.weight", (latent, ENC_FLAT), "w_mu"), ("encoder.var.bias", (latent,), "b")]
     for i, (ci, co) in zip((0, 2, 4, 6), ((256, 64), (64, 32), (32, 16), (16, 3))):
         out += [(f"decoder.features.{i}.weight", (ci, co, 2, 2), "w_convt"), (f"decoder.features.{i}.bias", (co,), "b")]
-    out += _swin_spec("embedder.") + _convnext_spec("convnext_backbone.") + _hybrid_spec("convnext_backbone.")
+    out += _swin_spec("embedder.", sw) + _convnext_spec("convnext_backbone.", cn) + _hybrid_spec("convnext_backbone.", sw)
     out += [("fc.weight", (500, 2000), "w_head1"), ("fc.bias", (500,), "b"),
             ("fc3.weight", (500, 1000), "w"), ("fc3.bias", (500,), "b"),
             ("fc2.weight", (2, 500), "w_head2"), ("fc2.bias", (2,), "b_head2")]
@@ -165,7 +171,7 @@ def make_tensor(name, shape, kind, seed=0, skip_big=False):
     raise ValueError(kind)
 
 
-def make_state_dict(net: str, seed: int = 0, latent: int = LATENT, skip_var: bool = False):
+def make_state_dict(net: str, seed: int = 0, latent: int = LATENT, skip_var: bool = False, size: str = "tiny"):
     """Seeded state_dict with the reference layout.  ``net`` in {'ed','vae'}.
 
     Swin tensors appear under both ``embedder.*`` and
@@ -173,7 +179,7 @@ def make_state_dict(net: str, seed: int = 0, latent: int = LATENT, skip_var: boo
     (same module object, reference genconvit_ed.py:69-70).  ``skip_var`` zero-fills
     ``encoder.var.weight`` (a 1.2 GiB tensor that only feeds the ``kl`` side effect).
     """
-    spec = ed_spec() if net == "ed" else vae_spec(latent)
+    spec = ed_spec(size) if net == "ed" else vae_spec(latent, size)
     sd = OrderedDict()
     aliases = []
     for name, shape, kind in spec:

@@ -46,6 +46,23 @@ def test_state_dict_layout_is_the_reference_layout(net):
     assert sd["embedder.layers.0.blocks.0.attn.relative_position_index"].dtype == torch.int64
 
 
+def test_large_variant_state_dict_layout():
+    """--s large (reference prediction.py:314-318 rewrites config['model'] to convnext_large / swin_large_...)."""
+    from model.genconvit_ed import GenConViTED
+    from oracle import weights as W
+    cfg = _config()
+    cfg["model"] = dict(cfg["model"], backbone="convnext_large", embedder="swin_large_patch4_window7_224", type="large")
+    with torch.device("meta"):
+        m = GenConViTED(cfg)
+    spec = W.ed_spec("large")
+    sd = m.state_dict()
+    assert set(sd) == {n for n, _, _ in spec}
+    for n, shape, _ in spec:
+        assert tuple(sd[n].shape) == tuple(shape), n
+    assert sd["backbone.stages.2.blocks.26.mlp.fc1.weight"].shape == (3072, 768)
+    assert sd["embedder.layers.2.blocks.17.attn.qkv.weight"].shape == (2304, 768)
+
+
 def test_strict_load_of_reference_shaped_checkpoint_and_dtype_switch(sd_ed):
     from model.genconvit_ed import GenConViTED
     from genconvit_b200.modules import compute_dtype_of
@@ -62,7 +79,7 @@ def test_unsupported_backbones_and_missing_weights_raise():
     from genconvit_b200.modules import create_model
     from model.genconvit import GenConViT
     with pytest.raises(NotImplementedError):
-        create_model("convnext_large")
+        create_model("convnext_base")             # the reference only ever selects tiny / large (prediction.py:314-318)
     cwd = os.getcwd()
     os.chdir("/tmp")
     try:

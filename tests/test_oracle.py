@@ -9,14 +9,14 @@ from oracle import nets
 from oracle import weights as W
 
 
-def _convnext_to_torchvision(sd):
+def _convnext_to_torchvision(sd, cfg=B.CONVNEXT_TINY):
     m = {}
     for wb in ("weight", "bias"):
         m[f"features.0.0.{wb}"] = sd[f"stem.0.{wb}"]
         m[f"features.0.1.{wb}"] = sd[f"stem.1.{wb}"]
         m[f"classifier.0.{wb}"] = sd[f"head.norm.{wb}"]
         m[f"classifier.2.{wb}"] = sd[f"head.fc.{wb}"]
-    for s, d in enumerate(B.CONVNEXT_TINY["depths"]):
+    for s, d in enumerate(cfg["depths"]):
         if s > 0:
             for j in (0, 1):
                 for wb in ("weight", "bias"):
@@ -30,14 +30,14 @@ def _convnext_to_torchvision(sd):
     return m
 
 
-def _swin_to_torchvision(sd):
+def _swin_to_torchvision(sd, cfg=B.SWIN_TINY):
     m = {}
     for wb in ("weight", "bias"):
         m[f"features.0.0.{wb}"] = sd[f"patch_embed.proj.{wb}"]
         m[f"features.0.2.{wb}"] = sd[f"patch_embed.norm.{wb}"]
         m[f"norm.{wb}"] = sd[f"norm.{wb}"]
         m[f"head.{wb}"] = sd[f"head.{wb}"]
-    for l, d in enumerate(B.SWIN_TINY["depths"]):
+    for l, d in enumerate(cfg["depths"]):
         for k in range(d):
             p, q = f"layers.{l}.blocks.{k}.", f"features.{1 + 2 * l}.{k}."
             for a, b in (("norm1", "norm1"), ("norm2", "norm2"), ("attn.qkv", "attn.qkv"), ("attn.proj", "attn.proj"),
@@ -69,6 +69,26 @@ def test_swin_matches_torchvision_bit_exact():
     tv = torchvision.models.swin_t(weights=None).eval()
     tv.load_state_dict(_swin_to_torchvision(sd), strict=True)
     x = W.synthetic_frames(2, 6)
+    with torch.no_grad():
+        assert torch.equal(B.swin_forward(sd, "", x), tv(x))
+
+
+def test_large_backbones_match_torchvision_bit_exact():
+    """The '--s large' variants (reference prediction.py:314-318): convnext_large against torchvision's own
+    convnext_large, swin_large_patch4_window7_224 against torchvision's SwinTransformer built with the large
+    hyper-parameters (embed 192, depths 2/2/18/2, heads 6/12/24/48; torchvision ships no swin_l constructor)."""
+    sd = {n: W.make_tensor(n, s, k, 3) for n, s, k in W._convnext_spec("", B.CONVNEXT_LARGE)}
+    tv = torchvision.models.convnext_large(weights=None).eval()
+    tv.load_state_dict(_convnext_to_torchvision(sd, B.CONVNEXT_LARGE), strict=True)
+    x = W.synthetic_frames(1, 5)
+    with torch.no_grad():
+        assert torch.equal(B.convnext_forward(sd, "", x), tv(x))
+    del tv, sd
+    from torchvision.models.swin_transformer import SwinTransformer
+    sd = {n: W.make_tensor(n, s, k, 3) for n, s, k in W._swin_spec("", B.SWIN_LARGE)}
+    tv = SwinTransformer(patch_size=[4, 4], embed_dim=192, depths=[2, 2, 18, 2], num_heads=[6, 12, 24, 48],
+                         window_size=[7, 7], stochastic_depth_prob=0.0).eval()
+    tv.load_state_dict(_swin_to_torchvision(sd, B.SWIN_LARGE), strict=True)
     with torch.no_grad():
         assert torch.equal(B.swin_forward(sd, "", x), tv(x))
 

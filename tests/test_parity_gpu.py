@@ -335,6 +335,31 @@ def test_packed_weights_follow_parent_load_state_dict_and_inplace_edits(sd_ed):
         assert (c - b - 1.0).abs().max().item() <= 2e-3
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_large_backbones_ed_matches_oracle(mode):
+    """--s large (reference prediction.py:314-318): GenConViT-ED on convnext_large / swin_large_patch4_window7_224,
+    N = 2, against the oracle (whose large backbones are pinned bit-exactly against torchvision)."""
+    from model.genconvit_ed import GenConViTED
+    from oracle import backbones, nets
+    from oracle.weights import make_state_dict, synthetic_frames
+    cfg = _config()
+    cfg["model"] = dict(cfg["model"], backbone="convnext_large", embedder="swin_large_patch4_window7_224", type="large")
+    sd = make_state_dict("ed", 0, size="large")
+    m = GenConViTED(cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).set_compute_dtype(mode)
+    x = synthetic_frames(2, 13)
+    with torch.no_grad():
+        want = nets.ed_forward(sd, x)
+        got = m(x.to(DEV)).float().cpu()
+        err = (got - want).abs().max().item()
+        assert err <= TOL[mode], f"ED large {mode}: {err:.3e}"
+        if mode == "fp32":
+            e_want = backbones.swin_forward(sd, "embedder.", x)
+            e_got = m.embedder(x.to(DEV)).float().cpu()
+            assert (e_got - e_want).abs().max().item() <= 1e-4 * max(1.0, e_want.abs().max().item())
+
+
 def test_cuda_graph_replay_matches_eager(ed_model):
     from oracle.weights import synthetic_frames
     ed_model.set_compute_dtype("bf16")
