@@ -74,6 +74,29 @@ class GenConViT(nn.Module):
                 m.set_compute_dtype(dt)
         return self
 
+    # Tensors no GenConViT forward ever reads: the VAE's second latent head and its two
+    # leftover Linear layers, fc3, and the Swin embedder with its HybridEmbed wrapper.  ~1.5 GB in fp32.
+    _UNUSED = ("model_vae.encoder.var.", "model_vae.encoder.fc1.", "model_vae.encoder.fc2.", "model_vae.fc3.",
+               "model_vae.embedder.", "model_vae.convnext_backbone.patch_embed.",
+               "model_ed.embedder.", "model_ed.backbone.patch_embed.")
+
+    def offload_unused_parameters(self, device="cpu"):
+        """Move the never-read tensors off the GPU (they stay in the ``state_dict``, on ``device``).  The reference's
+        ``.to(device)`` keeps them resident; this is an opt-in memory saver for long-running scorers.  ``encoder.var``
+        stays when the ``kl`` side effect is switched on (``model_vae.compute_kl``).  Returns the bytes moved."""
+        moved = 0
+        keep_var = getattr(getattr(self, "model_vae", None), "compute_kl", False)
+        seen = set()
+        for name, t in list(self.named_parameters(remove_duplicate=False)) + list(self.named_buffers(remove_duplicate=False)):
+            if not name.startswith(self._UNUSED) or (keep_var and ".encoder.var." in name):
+                continue
+            if id(t) in seen or t.device == torch.device(device):
+                continue
+            seen.add(id(t))
+            moved += t.numel() * t.element_size()
+            t.data = t.data.to(device)
+        return moved
+
     def forward_parts(self, x, eps=None):
         """The two networks' fp32 logits (ED [N,2] | None, VAE [N,2] | None) without the reference's concatenation:
         the bulk runtime scores straight from both buffers (gcv_score_videos_pair).  ``x``: fp32 NCHW on the GPU."""

@@ -153,3 +153,21 @@ def test_gather_scores_world_size_2_gloo():
         flat = out.permute(1, 0, 2).reshape(2, 6)          # ranks are contiguous video shards
         assert torch.equal(flat[0], torch.arange(6).float() % 2)
         assert torch.allclose(flat[1], torch.arange(6).float() / 10)
+
+
+def test_audit_checkpoint_tool_reports_renamed_and_misshapen_keys(sd_ed, tmp_path, capsys):
+    """tools/audit_checkpoint.py: first-contact check for real weights (timm-owned key names are restated, not verified)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("audit_checkpoint", os.path.join(ROOT, "tools", "audit_checkpoint.py"))
+    audit = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(audit)
+    torch.save(sd_ed, tmp_path / "good.pth")
+    assert audit.main([str(tmp_path / "good.pth"), "--net", "ed"]) == 0
+    bad = {k.replace("mlp.fc1", "mlp.linear1"): v for k, v in sd_ed.items()}
+    bad["fc.weight"] = torch.zeros(500, 1000)
+    torch.save({"state_dict": bad, "epoch": 3}, tmp_path / "bad.pth")
+    capsys.readouterr()
+    assert audit.main([str(tmp_path / "bad.pth"), "--net", "ed", "--max-list", "2"]) == 1
+    out = capsys.readouterr().out
+    assert "wrapped {state_dict: ...}" in out and "~ backbone.stages.0.blocks.0.mlp.linear1.weight" in out
+    assert "fc.weight: file (500, 1000), expected (500, 2000)" in out and "would FAIL" in out
