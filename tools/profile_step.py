@@ -14,6 +14,8 @@ from genconvit_b200.runtime import VideoScorer  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--tags-out", default="")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
@@ -23,11 +25,16 @@ model = bench.build_model({"bf16": torch.bfloat16, "fp16": torch.float16}[args.d
 sc = VideoScorer(model, args.batch, 16, use_graph=False)
 sc.x_static.normal_().clamp_(-2.1, 2.6)
 with torch.no_grad():
-    for _ in range(3):
+    for _ in range(args.steps):
         lib.profile = []
         sc._step()
         torch.cuda.synchronize()
         prof, lib.profile = lib.profile, None
+if args.tags_out:
+    # launch order of one step with each launch's shape tag and algorithmic work (FLOPs for the GEMM kernels, bytes for
+    # the others): zipped with an `ncu -k regex:gcv` capture of the same program by tools/ncu_step_traffic.py
+    import json
+    json.dump([[name, tag, work] for name, work, _s, _e, tag in prof], open(args.tags_out, "w"))
 rows = {}
 for name, work, s, e, tag in prof:
     r = rows.setdefault((name, tag), [0, 0.0, 0.0])
