@@ -360,6 +360,87 @@ def test_large_backbones_ed_matches_oracle(mode):
             assert (e_got - e_want).abs().max().item() <= 1e-4 * max(1.0, e_want.abs().max().item())
 
 
+@pytest.mark.parametrize("size", [(192, 160), (96, 224)])
+def test_ed_other_frame_sizes_vs_oracle(ed_model, sd_ed, size):
+    """GenConViT-ED is fully convolutional up to the global pool (any H, W that are multiples of 32): feature maps whose
+    widths are not multiples of the kernels' 8-column tiles (48/24/12/6, 40/20/10/5, 3) and non-square frames."""
+    from oracle import nets
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(3, 3, *size, generator=g).clamp_(-2.1, 2.6)
+    with torch.no_grad():
+        want = nets.ed_forward(sd_ed, x)
+        for mode in ("fp32", "fp16"):
+            got = ed_model.set_compute_dtype(mode)(x.to(DEV)).float().cpu()
+            err = (got - want).abs().max().item()
+            assert err <= TOL[mode], f"ED {size} {mode}: {err:.3e}"
+
+
+def test_vae_rejects_other_frame_sizes(vae_model):
+    """The VAE's Linear(128*14*14 -> latent) fixes 224x224 (reference: a shape error in nn.Linear); no silent garbage."""
+    vae_model.set_compute_dtype("fp16")
+    with pytest.raises(ValueError, match="224"):
+        vae_model(torch.zeros(2, 3, 192, 192, device=DEV))
+
+
+def test_forward_parts_and_pair_scoring_match_the_concatenated_path(full_model):
+    """runtime path: GenConViT.forward_parts + gcv_score_videos_pair == forward (torch.cat) + gcv_score_videos."""
+    from genconvit_b200 import engine, lib as L
+    from oracle.weights import synthetic_eps, synthetic_frames
+    n, fpv = 32, 16
+    x, eps = synthetic_frames(n, 141).to(DEV), synthetic_eps(n, 142).to(DEV)
+    full_model.set_compute_dtype("fp16")
+    with torch.no_grad():
+        rows = full_model(x, eps=eps).float().contiguous()
+        x1, x2 = full_model.forward_parts(x, eps)
+        assert torch.equal(torch.cat((x1, x2)), rows)
+        _, cls, val = engine.score_videos(rows, 2, n, fpv)
+        out = torch.empty((2, n // fpv), dtype=torch.float32, device=DEV)
+        L.score_videos_pair(x1, x2, n, fpv, out)
+        assert torch.equal(out[0], cls.float()) and torch.equal(out[1], val)
+        out1 = torch.empty_like(out)
+        L.score_videos_pair(x1, None, n, fpv, out1)           # single-network model
+        _, c1, v1 = engine.score_videos(x1.contiguous(), 1, n, fpv)
+        assert torch.equal(out1[0], c1.float()) and torch.equal(out1[1], v1)
+
+
+def test_video_scorer_uint8_ingest_matches_preprocess_then_forward(full_model):
+    """VideoScorer.submit with raw uint8 NHWC crops == model.pred_func.preprocess_frame (reference :95-108) followed by
+    the forward: same classes, same scores bit for bit (the GPU normalisation is bit-identical to the host arithmetic)."""
+    import numpy as np
+    from genconvit_b200.runtime import VideoScorer
+    from model import pred_func
+    from oracle.weights import synthetic_eps
+    n, fpv = 32, 16
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, size=(n, 224, 224, 3), dtype=np.uint8)
+    eps = synthetic_eps(n, 151).to(DEV)
+    full_model.set_compute_dtype("fp16")
+    sc = VideoScorer(full_model, n, fpv, eps=eps, use_graph=True)
+    cls, val = sc.score(torch.from_numpy(frames).pin_memory())
+    full_model.model_vae.set_epsilon(eps)
+    try:
+        c2, v2 = pred_func.pred_videos(pred_func.preprocess_frame(frames), full_model, fpv)
+    finally:
+        full_model.model_vae.set_epsilon(None)
+    assert torch.equal(cls, c2) and torch.equal(val, v2)
+
+
+def test_offload_unused_parameters_keeps_the_logits(full_model):
+    from oracle.weights import synthetic_eps, synthetic_frames
+    x, eps = synthetic_frames(4, 161).to(DEV), synthetic_eps(4, 162).to(DEV)
+    full_model.set_compute_dtype("fp16")
+    with torch.no_grad():
+        before = full_model(x, eps=eps).clone()
+        moved = full_model.offload_unused_parameters()
+        assert moved > 1_200_000_000                       # encoder.var alone is 1.26 GB in fp32
+        assert full_model.model_vae.encoder.var.weight.device.type == "cpu"
+        assert next(full_model.parameters()).is_cuda       # pred_vid's device discovery (pred_func.py:114) still works
+        assert torch.equal(full_model(x, eps=eps), before)
+        sd = full_model.state_dict()
+        assert "model_vae.encoder.var.weight" in sd and len(sd) == 588 + 614
+        full_model.to(DEV)
+
+
 def test_cuda_graph_replay_matches_eager(ed_model):
     from oracle.weights import synthetic_frames
     ed_model.set_compute_dtype("bf16")
