@@ -28,6 +28,8 @@
 //   * C = 96: W1 and W2 (147 KB) are loaded ONCE per CTA and stay resident in shared memory; only the y block of the
 //     next tile (double-buffered) is streamed.  C = 192 keeps streaming its 590 KB of weights through the slot ring,
 //     which the freed H buffers make deeper.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -67,7 +69,10 @@ struct Cfg {
   static constexpr int XBUF = RESIDENT ? 2 : 1;  // streamed weights: fc1 runs two chunks ahead, which hides the reload of the single y buffer
   static constexpr int OBUF = (2 * FCH + FCH / 2 + 2 * C <= 512) ? 2 : 1;
   static constexpr int STAGE_WARPS = 4 * (C / 32 < 4 ? C / 32 : 4);     // epilogue warps that drain output columns
-  static constexpr int STAGE_BYTES = STAGE_WARPS * 32 * 64;  // per-warp 32 x 64 B output staging tiles
+  // one 32-row x 64-byte staging tile per (32-column chunk of the output, TMEM lane quarter): the TMA producer drops the
+  // tile's RESIDUAL rows there (same swizzle as the drain uses), the drain adds the accumulator in place and stores
+  static constexpr int STAGE_TILES = 4 * (C / 32);
+  static constexpr int STAGE_BYTES = STAGE_TILES * 32 * 64;
   static constexpr int VEC_BYTES = ((2 * HC + 2 * C) * 4 + 1023) / 1024 * 1024;   // b1, colsum1 (LN fold), b2, gamma
   static constexpr int SMEM = kFCtrl + VEC_BYTES + XBUF * X_BYTES + W_BYTES + RING * SLOT + STAGE_BYTES + 1024;
   static_assert(C % 32 == 0 && C <= 192 && HC % FCH == 0 && NCH >= 2, "unsupported width");
@@ -87,6 +92,8 @@ struct FParams {
   const float* ln_stats;   // folded LayerNorm (LN = true): [M][C/32] x (sum, sumsq) of the y rows; colsum1 [4C]
   const float* colsum1;
   float ln_eps;
+  int debug;               // GCV_FUSED_DEBUG what-if switches (results are garbage): 1 = no GELU math, 2 = no residual
+                           // loads, 3 = no output stores, 4 = no drain at all, 5 = no LN-statistics loads
 };
 
 #ifdef GCV_FUSED_TRACE
@@ -128,7 +135,7 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 template <typename T, int C, bool LN>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w1,
-                 const __grid_constant__ CUtensorMap tm_w2, const FParams p) {
+                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x, const FParams p) {
   using K = Cfg<C>;
   constexpr int NRING = K::RING > 0 ? K::RING : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -146,6 +153,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
   uint64_t* h_empty = bars + 13;      // [2]  fc2 of chunk g has read it: barrier g & 1 (each epilogue group then waits on
                                       //      consecutive phases of ONE barrier -- parity waits must not skip a phase)
   uint64_t* w_full = bars + 15;       // [1]  resident weights have landed
+  uint64_t* res_full = bars + 16 + 2 * NRING + 1;    // [1]  the tile's residual rows are in the staging tiles
+  uint64_t* res_empty = res_full + 1;                // [1]  every draining warp has stored the tile
   uint64_t* ring_full = bars + 16;    // [RING]
   uint64_t* ring_empty = bars + 16 + NRING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * NRING);
@@ -176,6 +185,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     mbar_init(smem_u32(h_empty + 0), 1);
     mbar_init(smem_u32(h_empty + 1), 1);
     mbar_init(smem_u32(w_full), 1);
+    mbar_init(smem_u32(res_full), 1);
+    mbar_init(smem_u32(res_empty), K::STAGE_WARPS);
     for (int i = 0; i < K::RING; ++i) {
       mbar_init(smem_u32(ring_full + i), 1);
       mbar_init(smem_u32(ring_empty + i), 1);
@@ -224,6 +235,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         }
         __syncwarp();
       };
+      // the residual rows of tile ti ([128, C] of x) go into the staging tiles once the drain of tile ti-1 has left them
+      const uint32_t stage_smem = ring_smem + K::RING * K::SLOT;
+      auto issue_res = [&](int ti) {
+        mbar_wait(smem_u32(res_empty), ((uint32_t)ti & 1) ^ 1);
+        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(res_full), K::STAGE_BYTES);
+#pragma unroll 1
+          for (int t = 0; t < K::STAGE_TILES; ++t)       // tile t = (column chunk t >> 2, lane quarter t & 3)
+            tma_load_2d(stage_smem + t * 2048, &tm_x, smem_u32(res_full), (t >> 2) * 32, tile * FM + (t & 3) * 32);
+        }
+        __syncwarp();
+      };
       if (my_tiles > 0) issue_x(0);
       if constexpr (K::RESIDENT) {
         // both weight matrices, once: W1 chunk j = rows [128 j, 128 j + 128) in XKB K-blocks; W2 chunk j = columns
@@ -242,9 +266,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           }
         }
         __syncwarp();
-        // y blocks a tile ahead (two buffers)
+        // y blocks stay two tiles ahead of the residual rows: residual(ti) has to wait for the drain of tile ti-1 (which
+        // runs a chunk into tile ti), and nothing the MMA warp needs may queue behind that wait
+        if (my_tiles > 1) issue_x(1);
 #pragma unroll 1
-        for (int ti = 1; ti < my_tiles; ++ti) issue_x(ti);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          issue_res(ti);
+          if (ti + 2 < my_tiles) issue_x(ti + 2);
+        }
       } else {
 #pragma unroll 1
         for (int g = 0; g < total + 2; ++g) {          // same order as the MMA warp: W1 of chunk g, then W2 of chunk g-2
@@ -265,6 +294,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
             }
             // next tile's y block: as soon as this tile's fc1s can retire
             if (ti + 1 < my_tiles && j == K::NCH - 1) issue_x(ti + 1);
+            // this tile's residual rows, two chunks before its drain starts (the previous tile's drain is long over, so
+            // the wait inside never holds up the weight stream)
+            if (j == K::NCH - 2) issue_res(ti);
           }
           if (g >= 2) {
             const int gj = g - 2, jj = gj % K::NCH;
@@ -406,38 +438,39 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
     const int half = ((warp - 2) >> 2) & 1;  // which 64 hidden columns (2 K-blocks) of the group's chunk
     const int s = (warp - 2) >> 2;           // column-chunk phase of the O epilogue
     const int row = q * 32 + lane;
-    // output staging tile of this warp (dedicated: the drain of tile t overlaps the next tile's chunks); only the warps
-    // that own output columns (s < C / 32) have one
-    uint8_t* my_stage = stage_gen + (s * 4 + q) * (32 * 64);
     T* xg = reinterpret_cast<T*>(p.x);
     // this warp's share of tile ti's output accumulator: + b2, * gamma, + residual, staged coalesced store (in place)
     auto drain_output = [&](int ti) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int ob = ti % K::OBUF;
       const int64_t m_warp = (int64_t)tile * FM + q * 32;
-      const int64_t m = m_warp + lane;
-      // ---- + b2, * gamma, + residual, staged coalesced store (in place on x) ----
-      // the residual rows come from HBM: fetch them before blocking on the accumulator
-      uint4 res[2][4];
-#pragma unroll
-      for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const int c = s + 4 * ci;
-          res[ci][gq] = make_uint4(0, 0, 0, 0);
-          if (c < C / 32 && m < p.M) res[ci][gq] = *reinterpret_cast<const uint4*>(xg + m * C + c * 32 + gq * 8);
-        }
-      mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
-      tc_fence_after();
-      if (s >= C / 32) {
+      if (p.debug == 4) {
+        mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(o_empty + ob));
+        if (s < C / 32) {
+          mbar_wait(smem_u32(res_full), (uint32_t)ti & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(res_empty));
+        }
+        return;
       }
+      // ---- + b2, * gamma, + residual, staged coalesced store (in place on x) ----
+      mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
+      tc_fence_after();
+      if (s >= C / 32) {                     // this warp owns no output columns: release the accumulator and leave
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(o_empty + ob));
+        return;
+      }
+      mbar_wait(smem_u32(res_full), (uint32_t)ti & 1);     // the residual rows of this tile sit in the staging tiles
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const int c = s + 4 * ci;
         if (c >= C / 32) break;
+        uint8_t* my_stage = stage_gen + (c * 4 + q) * (32 * 64);
         float v[32];
         {
           uint32_t r[32];
@@ -458,9 +491,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           float* w = v + gq * 8;
           const float4 b0 = *reinterpret_cast<const float4*>(vec_b2 + n), b1 = *reinterpret_cast<const float4*>(vec_b2 + n + 4);
           const float4 g0 = *reinterpret_cast<const float4*>(vec_g + n), g1 = *reinterpret_cast<const float4*>(vec_g + n + 4);
+          uint4* slot = reinterpret_cast<uint4*>(my_stage + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4));
           float rr[8];
           {
-            const uint4 rq = res[ci][gq];
+            const uint4 rq = p.debug == 2 ? make_uint4(0, 0, 0, 0) : *slot;      // residual row `lane`, columns n .. n+7
             float2 f;
             f = unpack2<T>(rq.x); rr[0] = f.x; rr[1] = f.y;
             f = unpack2<T>(rq.y); rr[2] = f.x; rr[3] = f.y;
@@ -475,7 +509,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           uint4 pk;
           pk.x = pack2<T>(y0.x, y0.y); pk.y = pack2<T>(y1.x, y1.y);
           pk.z = pack2<T>(y2.x, y2.y); pk.w = pack2<T>(y3.x, y3.y);
-          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4)) = pk;
+          *slot = pk;                                                        // in place: same thread, same 16 bytes
         }
         __syncwarp();
         const int piece = lane & 3;
@@ -483,13 +517,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + (lane >> 2);
           const int64_t mm = m_warp + r;
-          if (mm < p.M) {
+          if (mm < p.M && p.debug != 3) {
             const uint4 pk = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
             *reinterpret_cast<uint4*>(xg + mm * C + n0 + piece * 8) = pk;
           }
         }
         __syncwarp();
       }
+      // the staging tiles of this warp may take the next tile's residual rows: this warp's generic-proxy writes / reads
+      // are ordered before the producer's next bulk copy into them
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(res_empty));
     };
     int pending = -1;
     int ln_ti = -1;
@@ -512,13 +551,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         if (ti != ln_ti) {
           if (ln_ti < 0) {
             const int64_t m = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + row;
-            if (m < p.M) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
+            if (m < p.M && p.debug != 5) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
           }
           lnrs = ln_row_finish(ln_raw, C / 32, C, p.ln_eps);
           lnrs.x *= 0.5f; lnrs.y *= 0.5f;
           ln_ti = ti;
           const int64_t mn = (int64_t)((int)blockIdx.x + (ti + 1) * (int)gridDim.x) * FM + row;
-          if (mn < p.M) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
+          if (mn < p.M && p.debug != 5) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
         }
       }
       const uint32_t n_use = (uint32_t)(g >> 1);
@@ -542,6 +581,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         }
         const float* bj = vec_b1 + j * FCH + kb * 32;
         uint4 pk[4];
+        if (p.debug == 1) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            pk[gq] = make_uint4(__float_as_uint(v[gq * 8]), __float_as_uint(v[gq * 8 + 2]), __float_as_uint(v[gq * 8 + 4]), __float_as_uint(v[gq * 8 + 6]));
+        } else
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           if constexpr (LN) {
@@ -573,15 +617,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       if (pending >= 0) { drain_output(pending); pending = -1; }
       if ((g + 2) / K::NCH != ti) {                   // that was this group's last chunk of tile ti
         pending = ti;
-        // the drain reads the tile's residual rows from HBM: pull this warp's 32 rows into L2 a chunk ahead
-        const int64_t m_warp = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + q * 32;
-        const uint8_t* rbase = reinterpret_cast<const uint8_t*>(xg + m_warp * C);
-        const int64_t rbytes = (p.M - m_warp < 32 ? (p.M - m_warp > 0 ? p.M - m_warp : 0) : 32) * (int64_t)(C * 2);
-#pragma unroll
-        for (int i = 0; i < (32 * C * 2) / (128 * 32); ++i) {
-          const int64_t off = (int64_t)(i * 32 + lane) * 128;
-          if (off < rbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(rbase + off));
-        }
       }
     }
     if (pending >= 0) drain_output(pending);
@@ -640,6 +675,8 @@ int launch_fused_impl(int dtype, const void* y, const void* w1, const void* w2, 
   if (rc) return rc;
   if ((rc = fused_map(&m1, dtype, w1, K::HC, C, FCH))) return rc;
   if ((rc = fused_map(&m2, dtype, w2, C, K::HC, C))) return rc;
+  CUtensorMap mx;                      // residual rows: 32-column x 32-row boxes of x [M, C], same 64B swizzle as the drain's staging
+  if ((rc = fused_map(&mx, dtype, p.x, p.M, C, 32))) return rc;
   static unsigned long long attr_devs = 0;
   if (first_on_device(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<T, C, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
@@ -650,7 +687,7 @@ int launch_fused_impl(int dtype, const void* y, const void* w1, const void* w2, 
   }
   const int sms = device_sms();
   const int grid = p.tiles < sms ? p.tiles : sms;
-  mlp_fused_kernel<T, C, LN><<<grid, kFThreads, K::SMEM, stream>>>(my, m1, m2, p);
+  mlp_fused_kernel<T, C, LN><<<grid, kFThreads, K::SMEM, stream>>>(my, m1, m2, mx, p);
   return check_launch("mlp_fused");
 }
 
@@ -690,6 +727,11 @@ int mlp_fused(int dtype, const void* y, const float* ln_stats, float ln_eps, con
   p.idesc2 = umma_idesc_f16(dtype == GCV_BF16, FM, C);
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.x = x;
   p.ln_stats = ln_stats; p.colsum1 = colsum1; p.ln_eps = ln_eps;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GCV_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   if (dtype == GCV_BF16) {
     return C == 96 ? launch_fused<__nv_bfloat16, 96>(dtype, y, w1, w2, p, stream)
                    : launch_fused<__nv_bfloat16, 192>(dtype, y, w1, w2, p, stream);

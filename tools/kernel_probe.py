@@ -71,6 +71,17 @@ if args.which in ("fc2", "all"):
         x = torch.randn(M, C, device=dev).to(dt)
         timed(f"fc2+res M{M} N{C} K{4 * C}",
               lambda: L.gemm(a, w, x, M, C, 4 * C, bias=bias, gamma=gamma, residual=x, ldr=C), 2.0 * M * 4 * C * C / 1e3, "TF/s")
+if args.which in ("fusedln",):
+    dtl = torch.float16
+    for (T, C) in ((3136, 96), (784, 192)):
+        M = B * T
+        y = torch.randn(M, C, device=dev).to(dtl)
+        x = torch.randn(M, C, device=dev).to(dtl)
+        w1 = (torch.randn(4 * C, C, device=dev) / C ** 0.5).to(dtl)
+        w2 = (torch.randn(C, 4 * C, device=dev) / (4 * C) ** 0.5).to(dtl)
+        st = torch.rand(M, C // 32, 2, device=dev) + 1.0
+        b1, cs, b2, g = torch.randn(4 * C, device=dev), torch.randn(4 * C, device=dev), torch.randn(C, device=dev), torch.rand(C, device=dev) * 0.1
+        timed(f"mlp_fused_ln M{M} C{C}", lambda: L.mlp_fused_ln(y, st, 1e-6, w1, b1, cs, w2, b2, g, x, M, C), 16.0 * M * C * C / 1e3, "TF/s")
 if args.which in ("fused", "all"):
     for (T, C) in ((3136, 96), (784, 192)):
         M = B * T
