@@ -75,6 +75,8 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
 int score_videos_pair(const float* la, const float* lb, int n_frames, int fpv, float* out, cudaStream_t stream);
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
+int convt2x2_mma(int dtype, const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                 int act, int B, int H, int W, int CI, int tail, cudaStream_t stream);
 int swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C, int heads,
                           int shift, cudaStream_t stream);
 int swin_patch_merge(int dtype, const void* x, void* out, int B, int res, int C, cudaStream_t stream);
@@ -218,6 +220,10 @@ int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                        int CI, int CO, void* stream) {
   return convt2x2_small(dtype, x, y, w, bias, act, B, H, W, CI, CO, S(stream));
+}
+int gcv_convt2x2_mma(int dtype, const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                     int act, int B, int H, int W, int CI, int tail, void* stream) {
+  return convt2x2_mma(dtype, x, y, w1, b1, w2, b2, act, B, H, W, CI, tail, S(stream));
 }
 int gcv_swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C,
                               int heads, int shift, void* stream) {

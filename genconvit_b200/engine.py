@@ -303,24 +303,34 @@ def _pack_conv3x3(w, dev, dt):
 
 def _pack_convt(w, b, dev, dt):
     """ConvTranspose2d k2 s2 weight [Ci,Co,2,2] -> GEMM B [(i,j,co), Ci] and the bias repeated per tap.
-    The 16 -> 3 output layer runs on the streaming kernel, which takes fp32 weights."""
+    The 16 -> 3 output layer is also kept in fp32 for the streaming kernel (third entry; None for the others)."""
     co = w.shape[1]
-    if (w.shape[0], co) == (16, 3):
-        dt = torch.float32
-    return _cd(w.permute(2, 3, 1, 0).reshape(4 * co, w.shape[0]), dev, dt), _f32(b.repeat(4), dev)
+    wm = w.permute(2, 3, 1, 0).reshape(4 * co, w.shape[0])
+    return _cd(wm, dev, dt), _f32(b.repeat(4), dev), (_f32(wm, dev) if (w.shape[0], co) == (16, 3) else None)
 
 
 def _run_convt_stack(x, layers, b, h, w, act, dt, dev, backend):
-    """x: [B*h*w, Ci] tokens -> NHWC image after the k2s2 transposed-conv stack (pixel-shuffle epilogue)."""
-    for wt, bias in layers:
+    """x: [B*h*w, Ci] tokens -> NHWC image after the k2s2 transposed-conv stack.  Wide layers: tcgen05 GEMM with the
+    pixel-shuffle epilogue; 64 -> 32 and the fused 32 -> 16 -> 3 tail (16-bit modes): the HMMA kernel of convt_mma.cu."""
+    k = 0
+    while k < len(layers):
+        wt, bias, w32 = layers[k]
         co, ci = wt.shape[0] // 4, wt.shape[1]
+        small = dt != torch.float32 and (b * h * w) % 16 == 0 and backend == L.GEMM_AUTO
+        if small and (ci, co) == (32, 16) and k + 2 == len(layers) and layers[k + 1][2] is not None:
+            out = _empty((b * 16 * h * w, 3), dt, dev)
+            L.convt2x2_mma(x, out, wt, bias, act, b, h, w, ci, w2=layers[k + 1][0], b2=layers[k + 1][1])
+            return out, 4 * h, 4 * w
         out = _empty((b * 4 * h * w, co), dt, dev)
-        if (ci, co) == (16, 3):
-            L.convt2x2_small(x, out, wt, bias, act, b, h, w, ci, co)
+        if w32 is not None:
+            L.convt2x2_small(x, out, w32, bias, act, b, h, w, ci, co)
+        elif small and (ci, co) in ((64, 32), (32, 16)):
+            L.convt2x2_mma(x, out, wt, bias, act, b, h, w, ci)
         else:
             L.gemm(x, wt, out, b * h * w, 4 * co, ci, bias=bias, act=act, store=L.STORE_PIXEL_SHUFFLE2,
                    ps=(h, w, co), backend=backend)
         x, h, w = out, 2 * h, 2 * w
+        k += 1
     return x, h, w
 
 

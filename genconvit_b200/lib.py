@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_convt2x2_mma", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -79,6 +79,7 @@ def load():
     lib.gcv_conv3x3_c32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.gcv_convt2x2_mma.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_score_videos.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
@@ -333,6 +334,19 @@ def maxpool2(x, y, B, H, W, Cc):
 def convt2x2_small(x, y, w, bias, act, B, H, W, ci, co):
     _run("convt2x2_small", B * H * W * (ci + 4.0 * co) * x.element_size(), lambda: load().gcv_convt2x2_small(
         DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), act, B, H, W, ci, co, _stream()))
+
+
+def convt2x2_mma(x, y, w1, b1, act, B, H, W, ci, w2=None, b2=None):
+    """ConvTranspose2d(ci -> ci/2, k2 s2) + act on HMMA; with (w2, b2) also the fused 16 -> 3 output layer.  See
+    gcv_convt2x2_mma."""
+    tail = w2 is not None
+    _need(x, B * H * W * ci, "convt2x2_mma x")
+    _need(y, B * H * W * (48 if tail else 2 * ci), "convt2x2_mma y")
+    _need(w1, 2 * ci * ci, "convt2x2_mma w1")
+    _run("convt2x2_mma", B * H * W * (ci + (48.0 if tail else 2.0 * ci)) * x.element_size(),
+         lambda: load().gcv_convt2x2_mma(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w1), _p(b1), _p(w2) if tail else None,
+                                         _p(b2) if tail else None, act, B, H, W, ci, int(tail), _stream()),
+         f"B{B} H{H} C{ci}" + ("+tail" if tail else ""))
 
 
 def resize2x_to_nchw(x, y, B, H, W, Cc):

@@ -183,6 +183,14 @@ int gcv_conv3x3_c32(int dtype, const void* x, void* y, const void* w, const floa
                     int pool, int B, int H, int W, void* stream);
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act,
                        int B, int H, int W, int CI, int CO, void* stream);
+/* gcv_convt2x2_mma: the decoders' small-channel layers ConvTranspose2d(CI -> CI/2, k2 s2) + act as a per-token
+ *   tensor-core product with a pixel-shuffle store (reference model/genconvit_ed.py:51-56, genconvit_vae.py:56-62):
+ *   x [B*H*W, CI] tokens, w1 [(i,j,co), CI] and b1 [4*CI/2] (bias repeated per tap) as for gcv_gemm's pixel-shuffle
+ *   mode, CI = 32 or 64, B*H*W a multiple of 16, 16-bit dtypes.  tail = 0: y [B,2H,2W,CI/2].  tail = 1 (CI = 32): also applies
+ *   the output layer ConvTranspose2d(16 -> 3) + act to the 16-channel result without storing it:
+ *   w2 [(i,j,c), 16] of `dtype`, b2 [12], y [B,4H,4W,3]. */
+int gcv_convt2x2_mma(int dtype, const void* x, void* y, const void* w1, const float* b1, const void* w2,
+                     const float* b2, int act, int B, int H, int W, int CI, int tail, void* stream);
 int gcv_resize2x_to_nchw(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
 int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W, int C, void* stream);
 

@@ -167,8 +167,7 @@ def test_gemm_pixel_shuffle_is_conv_transpose(cfg, dtype):
     x = _rand(B, ci, H, W, seed=1)
     w, bias = _rand(ci, co, 2, 2, seed=2, scale=ci ** -0.5), _rand(co, seed=3)
     want = F.leaky_relu(F.conv_transpose2d(x, w, bias, stride=2), 0.01).permute(0, 2, 3, 1)
-    wp, bp = _pack_convt(w, bias, DEV, dtype)
-    wp = wp.to(dtype)
+    wp, bp, _ = _pack_convt(w, bias, DEV, dtype)
     tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, ci).to(dtype).contiguous()
     out = torch.empty((B, 2 * H, 2 * W, co), device=DEV, dtype=dtype)
     L.gemm(tokens, wp, out, B * H * W, 4 * co, ci, bias=bp, act=L.ACT_LEAKY, store=L.STORE_PIXEL_SHUFFLE2, ps=(H, W, co))
@@ -186,12 +185,67 @@ def test_convt2x2_small_output_layer(dtype, act):
     w, bias = _rand(16, 3, 2, 2, seed=2, scale=0.25), _rand(3, seed=3)
     y = F.conv_transpose2d(x, w, bias, stride=2)
     want = (F.relu(y) if act == "relu" else F.leaky_relu(y, 0.01)).permute(0, 2, 3, 1)
-    wp, bp = _pack_convt(w, bias, DEV, dtype)
+    _, bp, wp = _pack_convt(w, bias, DEV, dtype)
     assert wp.dtype == torch.float32
     tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, 16).to(dtype).contiguous()
     out = torch.full((B, 2 * H, 2 * W, 3), float("nan"), device=DEV, dtype=dtype)
     L.convt2x2_small(tokens, out, wp, bp, L.ACT_RELU if act == "relu" else L.ACT_LEAKY, B, H, W, 16, 3)
     _close(out, want, TOL[dtype], "convt2x2_small")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(2, 8, 8, 64, "relu"), (3, 28, 28, 64, "leaky"), (1, 4, 12, 32, "relu"), (5, 56, 56, 32, "leaky")])
+def test_convt2x2_mma_small_channel_layers(cfg, dtype):
+    """ConvTranspose2d(64 -> 32) / (32 -> 16), k2 s2, + act on the HMMA kernel (genconvit_ed.py:51-55,
+    genconvit_vae.py:56-62) against torch's conv_transpose2d."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_convt
+    B, H, W, ci, act = cfg
+    co = ci // 2
+    x = _rand(B, ci, H, W, seed=1).to(dtype).float()
+    w, bias = _rand(ci, co, 2, 2, seed=2, scale=ci ** -0.5).to(dtype).float(), _rand(co, seed=3)
+    y = F.conv_transpose2d(x, w, bias, stride=2)
+    want = (F.relu(y) if act == "relu" else F.leaky_relu(y, 0.01)).permute(0, 2, 3, 1)
+    wp, bp, _ = _pack_convt(w, bias, DEV, dtype)
+    tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, ci).to(dtype).contiguous()
+    out = torch.full((B, 2 * H, 2 * W, co), float("nan"), device=DEV, dtype=dtype)
+    L.convt2x2_mma(tokens, out, wp, bp, L.ACT_RELU if act == "relu" else L.ACT_LEAKY, B, H, W, ci)
+    _close(out, want, TOL[dtype], f"convt2x2_mma {cfg}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(1, 8, 8, "relu"), (3, 28, 28, "leaky"), (1, 4, 12, "leaky"), (6, 56, 56, "relu")])
+def test_convt2x2_mma_fused_output_tail(cfg, dtype):
+    """The fused decoder tail ConvT(32 -> 16) + act + ConvT(16 -> 3) + act (genconvit_ed.py:53-57,
+    genconvit_vae.py:60-64): the 16-channel intermediate is rounded to the activation type like the stored tensor
+    it replaces, so the comparison target rounds it too."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_convt
+    B, H, W, act = cfg
+    f = F.relu if act == "relu" else (lambda v: F.leaky_relu(v, 0.01))
+    x = _rand(B, 32, H, W, seed=1).to(dtype).float()
+    w1, b1 = _rand(32, 16, 2, 2, seed=2, scale=32 ** -0.5).to(dtype).float(), _rand(16, seed=3)
+    w2, b2 = _rand(16, 3, 2, 2, seed=4, scale=0.25).to(dtype).float(), _rand(3, seed=5)
+    mid = f(F.conv_transpose2d(x, w1, b1, stride=2)).to(dtype).float()
+    want = f(F.conv_transpose2d(mid, w2, b2, stride=2)).permute(0, 2, 3, 1)
+    p1, q1, _ = _pack_convt(w1, b1, DEV, dtype)
+    p2, q2, _ = _pack_convt(w2, b2, DEV, dtype)
+    tokens = x.permute(0, 2, 3, 1).reshape(B * H * W, 32).to(dtype).contiguous()
+    out = torch.full((B, 4 * H, 4 * W, 3), float("nan"), device=DEV, dtype=dtype)
+    L.convt2x2_mma(tokens, out, p1, q1, L.ACT_RELU if act == "relu" else L.ACT_LEAKY, B, H, W, 32, w2=p2, b2=q2)
+    _close(out, want, TOL[dtype], f"convt2x2_mma tail {cfg}")
+
+
+def test_convt2x2_mma_rejects_unsupported_shapes():
+    L = _lib()
+    x = torch.zeros(2 * 7 * 7, 32, device=DEV, dtype=torch.float16)
+    y = torch.zeros(2 * 14 * 14, 16, device=DEV, dtype=torch.float16)
+    w, b = torch.zeros(64, 32, device=DEV, dtype=torch.float16), torch.zeros(64, device=DEV)
+    with pytest.raises(L.GcvError):
+        L.convt2x2_mma(x, y, w, b, L.ACT_RELU, 2, 7, 7, 32)            # 98 tokens: not whole 16-token tiles (GEMM path)
+    with pytest.raises(L.GcvError):
+        L.convt2x2_mma(torch.zeros(128, 32, device=DEV), torch.zeros(512, 16, device=DEV), w.float(), b, L.ACT_RELU,
+                       2, 8, 8, 32)                                    # fp32 mode keeps the GEMM path
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
