@@ -459,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
     peak_tf = float(peaks["bf16_tflops"])
     peak_tf_sustained = float(peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"])
     peak_gbs = float(peaks["hbm_gbs"])
-    tensor_kernels = ("gemm_tcgen05", "mlp_fused")
+    tensor_kernels = ("gemm_tcgen05", "mlp_fused", "conv3x3_tc")
 
     def roof(name, k):
         tensor = name in tensor_kernels or name.startswith("gemm")

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libgenconvit_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "mlp_fused.cu", "gemm_simt.cu", "convnext_ops.cu", "dwconv_mma.cu", "autoenc_ops.cu", "conv3x3_c16.cu", "conv3x3_c32.cu", "convt_mma.cu", "stem_fused.cu", "swin_ops.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "mlp_fused.cu", "gemm_simt.cu", "convnext_ops.cu", "dwconv_mma.cu", "autoenc_ops.cu", "conv3x3_c16.cu", "conv3x3_c32.cu", "conv3x3_tc.cu", "convt_mma.cu", "stem_fused.cu", "swin_ops.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -75,6 +75,9 @@ int score_videos(const float* logits, int n_nets, int n_frames, int fpv, float* 
 int score_videos_pair(const float* la, const float* lb, int n_frames, int fpv, float* out, cudaStream_t stream);
 int convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                    int CI, int CO, cudaStream_t stream);
+bool conv3x3_tc_supported(int dtype, int C, int N);
+int conv3x3_tc(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool, int B,
+               int H, int W, int C, int N, cudaStream_t stream);
 int convt2x2_mma(int dtype, const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                  int act, int B, int H, int W, int CI, int tail, cudaStream_t stream);
 int swin_window_attention(int dtype, const void* qkv, void* out, const float* bias_table, int B, int res, int C, int heads,
@@ -220,6 +223,11 @@ int gcv_nhwc_to_nchw_f32(int dtype, const void* x, float* y, int B, int H, int W
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act, int B, int H, int W,
                        int CI, int CO, void* stream) {
   return convt2x2_small(dtype, x, y, w, bias, act, B, H, W, CI, CO, S(stream));
+}
+int gcv_conv3x3_tc_supported(int dtype, int C, int N) { return conv3x3_tc_supported(dtype, C, N) ? 1 : 0; }
+int gcv_conv3x3_tc(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool,
+                   int B, int H, int W, int C, int N, void* stream) {
+  return conv3x3_tc(dtype, x, y, w, bias, stride, act, pool, B, H, W, C, N, S(stream));
 }
 int gcv_convt2x2_mma(int dtype, const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                      int act, int B, int H, int W, int CI, int tail, void* stream) {

@@ -379,6 +379,12 @@ class PackedED:
                 L.conv3x3_c32(e, nxt, wt, bias, 1, L.ACT_RELU, True, n, h, w)
                 e, h, w, c = nxt, h // 2, w // 2, co
                 continue
+            if backend == L.GEMM_AUTO and L.conv3x3_tc_supported(dt, c, co) and h % 2 == 0 and w % 2 == 0:
+                # 64 -> 128, 128 -> 256: tcgen05 implicit GEMM (TMA-gathered taps), ReLU + pool in the epilogue
+                nxt = _empty((n * (h // 2) * (w // 2), co), dt, dev)
+                L.conv3x3_tc(e, nxt, wt, bias, 1, L.ACT_RELU, True, n, h, w, c, co)
+                e, h, w, c = nxt, h // 2, w // 2, co
+                continue
             a = _empty((n * h * w, 9 * c), dt, dev)
             L.im2col3x3(e, a, n, h, w, c, 1)
             full = _empty((n * h * w, co), dt, dev)
@@ -474,6 +480,11 @@ class PackedVAE:
             if (c, co) == (32, 64) and dt != torch.float32:
                 nxt = _empty((n * h2 * w2, co), dt, dev)
                 L.conv3x3_c32(e, nxt, wt, bias, 2, L.ACT_LEAKY, False, n, h, w)
+                e, h, w, c = nxt, h2, w2, co
+                continue
+            if backend == L.GEMM_AUTO and L.conv3x3_tc_supported(dt, c, co):
+                nxt = _empty((n * h2 * w2, co), dt, dev)
+                L.conv3x3_tc(e, nxt, wt, bias, 2, L.ACT_LEAKY, False, n, h, w, c, co)
                 e, h, w, c = nxt, h2, w2, co
                 continue
             a = _empty((n * h2 * w2, 9 * c), dt, dev)

@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_convt2x2_mma", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_convt2x2_mma", "gcv_conv3x3_tc_supported", "gcv_conv3x3_tc", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -79,6 +79,8 @@ def load():
     lib.gcv_conv3x3_c32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.gcv_conv3x3_tc_supported.argtypes = [i32, i32, i32]
+    lib.gcv_conv3x3_tc.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_mma.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_resize2x_to_nchw.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_nhwc_to_nchw_f32.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
@@ -329,6 +331,24 @@ def conv3x3_c32(x, y, w, bias, stride, act, pool, B, H, W):
 def maxpool2(x, y, B, H, W, Cc):
     _run("maxpool2", 1.25 * B * H * W * Cc * x.element_size(), lambda: load().gcv_maxpool2(
         DTYPE_CODE[x.dtype], _p(x), _p(y), B, H, W, Cc, _stream()))
+
+
+def conv3x3_tc_supported(dt, c, n):
+    return dt in DTYPE_CODE and bool(load().gcv_conv3x3_tc_supported(DTYPE_CODE[dt], c, n))
+
+
+def conv3x3_tc(x, y, w, bias, stride, act, pool, B, H, W, ci, co):
+    """3x3 conv (+ act, + 2x2 max-pool) of the encoders' 64 -> 128 / 128 -> 256 layers as a tcgen05 implicit GEMM; see
+    gcv_conv3x3_tc."""
+    ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if pool:
+        ho, wo = ho // 2, wo // 2
+    _need(x, B * H * W * ci, "conv3x3_tc x")
+    _need(y, B * ho * wo * co, "conv3x3_tc y")
+    _need(w, 9 * ci * co, "conv3x3_tc w")
+    _run("conv3x3_tc", 2.0 * B * ((H - 1) // stride + 1) * ((W - 1) // stride + 1) * co * 9 * ci,
+         lambda: load().gcv_conv3x3_tc(DTYPE_CODE[x.dtype], _p(x), _p(y), _p(w), _p(bias), stride, act, int(bool(pool)),
+                                       B, H, W, ci, co, _stream()), f"B{B} H{H} C{ci} s{stride}")
 
 
 def convt2x2_small(x, y, w, bias, act, B, H, W, ci, co):

@@ -181,6 +181,14 @@ int gcv_conv3x3_c16(int dtype, const void* x, void* y, const void* w, const floa
  *   stride 1 + ReLU + 2x2 max-pool = genconvit_ed.py:22-24, stride 2 + LeakyReLU = genconvit_vae.py:22-24. */
 int gcv_conv3x3_c32(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act,
                     int pool, int B, int H, int W, void* stream);
+/* gcv_conv3x3_tc: the encoders' wide layers Conv2d(64 -> 128) / Conv2d(128 -> 256), k3 pad 1, as a tcgen05 implicit
+ *   GEMM (no im2col matrix: every tap's A tile is one 4-D TMA box of x, zero-filled outside the image):
+ *   x [B,H,W,C], C in {64,128}; w [N][(kh,kw,ci)] of `dtype`, N % 64 == 0, N <= 256; bias fp32 [N]; stride 1 + ReLU +
+ *   fused 2x2 max-pool = genconvit_ed.py:26-32, stride 2 + LeakyReLU (BatchNorm folded by the host) =
+ *   genconvit_vae.py:25-27.  y [B,Ho,Wo,N] (pool: [B,Ho/2,Wo/2,N]).  16-bit dtypes only. */
+int gcv_conv3x3_tc_supported(int dtype, int C, int N);
+int gcv_conv3x3_tc(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool,
+                   int B, int H, int W, int C, int N, void* stream);
 int gcv_convt2x2_small(int dtype, const void* x, void* y, const float* w, const float* bias, int act,
                        int B, int H, int W, int CI, int CO, void* stream);
 /* gcv_convt2x2_mma: the decoders' small-channel layers ConvTranspose2d(CI -> CI/2, k2 s2) + act as a per-token

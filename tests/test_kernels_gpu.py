@@ -647,3 +647,45 @@ def test_conv3x3_c32_direct(shape, dtype):
     out = torch.full((B, H, W, 64), float("nan"), device=DEV, dtype=dtype)
     L.conv3x3_c32(x, out, wp, b, 1, L.ACT_RELU, False, B, H, W)
     _close(out, want, TOL[dtype], "conv3x3_c32 s1 relu")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("cfg", [(2, 28, 28, 64, 128), (3, 14, 14, 128, 256), (5, 20, 12, 64, 128), (1, 8, 8, 128, 256),
+                                 (170, 28, 28, 64, 128), (7, 6, 6, 128, 64)])
+def test_conv3x3_tc_implicit_gemm(cfg, dtype):
+    """tcgen05 implicit-GEMM 3x3 conv (TMA-gathered taps, zero-filled padding) vs torch conv2d (fp32) on the same rounded
+    inputs: stride 1 + ReLU + 2x2 max-pool (genconvit_ed.py:26-32), stride 2 + LeakyReLU (genconvit_vae.py:25-27), and
+    stride 1 without pooling.  (170 frames x 8 tiles > one round of the 148 persistent CTAs: both accumulator stages
+    and the smem ring wrap.)"""
+    L = _lib()
+    from genconvit_b200.engine import _pack_conv3x3
+    B, H, W, ci, co = cfg
+    x = _rand(B, H, W, ci, dtype=dtype, seed=1)
+    w = _rand(co, ci, 3, 3, seed=2, scale=(9 * ci) ** -0.5)
+    b = _rand(co, seed=3, scale=0.1)
+    wp = _pack_conv3x3(w, DEV, dtype)
+    wr = wp.float().reshape(co, 3, 3, ci).permute(0, 3, 1, 2)
+    xin = x.float().permute(0, 3, 1, 2)
+    want = F.max_pool2d(F.relu(F.conv2d(xin, wr, b, padding=1)), 2).permute(0, 2, 3, 1)
+    out = torch.full((B, H // 2, W // 2, co), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_tc(x, out, wp, b, 1, L.ACT_RELU, True, B, H, W, ci, co)
+    _close(out, want, TOL[dtype], "conv3x3_tc s1 relu pool")
+    want = F.leaky_relu(F.conv2d(xin, wr, b, stride=2, padding=1), 0.01).permute(0, 2, 3, 1)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, Ho, Wo, co), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_tc(x, out, wp, b, 2, L.ACT_LEAKY, False, B, H, W, ci, co)
+    _close(out, want, TOL[dtype], "conv3x3_tc s2 leaky")
+    want = F.relu(F.conv2d(xin, wr, b, padding=1)).permute(0, 2, 3, 1)
+    out = torch.full((B, H, W, co), float("nan"), device=DEV, dtype=dtype)
+    L.conv3x3_tc(x, out, wp, b, 1, L.ACT_RELU, False, B, H, W, ci, co)
+    _close(out, want, TOL[dtype], "conv3x3_tc s1 relu")
+
+
+def test_conv3x3_tc_rejects_unsupported():
+    L = _lib()
+    assert not L.conv3x3_tc_supported(torch.float32, 64, 128)
+    assert not L.conv3x3_tc_supported(torch.float16, 32, 64)
+    x = torch.zeros(1, 7, 7, 64, device=DEV, dtype=torch.float16)
+    w, b = torch.zeros(128, 576, device=DEV, dtype=torch.float16), torch.zeros(128, device=DEV)
+    with pytest.raises(L.GcvError):                    # pooling needs even conv output sizes
+        L.conv3x3_tc(x, torch.zeros(1, 3, 3, 128, device=DEV, dtype=torch.float16), w, b, 1, L.ACT_RELU, True, 1, 7, 7, 64, 128)

@@ -44,6 +44,7 @@ for name, work, s, e, tag in prof:
 tot = sum(r[1] for r in rows.values())
 print(f"total {tot:.2f} ms over {len(prof)} launches")
 for (name, tag), (cnt, ms, work) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
-    rate = work / (ms / 1e3) / (1e12 if name.startswith("gemm") else 1e9)
-    unit = "TF/s" if name.startswith("gemm") else "GB/s"
+    tensor = name.startswith("gemm") or name in ("mlp_fused", "conv3x3_tc")     # these report FLOPs as their work
+    rate = work / (ms / 1e3) / (1e12 if tensor else 1e9)
+    unit = "TF/s" if tensor else "GB/s"
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}%  x{cnt:<3d} {ms / cnt:7.3f} ms/launch {rate:8.1f} {unit}  {name:18s} {tag}")
