@@ -64,6 +64,11 @@ int maxpool2(int dtype, const void* x, void* y, int B, int H, int W, int C, cuda
 int conv3x3_c32(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool, int B,
                 int H, int W, cudaStream_t stream);
 int ln_finalize(const float* stats, float* out, int64_t M, int chunks, int K, float eps, cudaStream_t stream);
+int stem_fused_src(int dtype, int src, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
+                   const float* ln_b, float eps, int B, int H, int W, const float* mean3, const float* std3,
+                   cudaStream_t stream);
+int conv3x3_first_src(int dtype, int u8, const void* x, void* y, const float* w, const float* b, int stride, int act,
+                      int pool, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t stream);
 int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
                const float* ln_b, float eps, int B, int H, int W, cudaStream_t stream);
 int conv3x3_c16(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool, int B,
@@ -199,6 +204,14 @@ int gcv_im2col3x3(int dtype, const void* x, void* a, int B, int H, int W, int C,
 int gcv_conv3x3_c16(int dtype, const void* x, void* y, const void* w, const float* bias, int stride, int act, int pool,
                     int B, int H, int W, void* stream) {
   return conv3x3_c16(dtype, x, y, w, bias, stride, act, pool, B, H, W, S(stream));
+}
+int gcv_stem_fused_u8(int dtype, const uint8_t* x, void* y, const void* w, const float* bias, const float* ln_w,
+                      const float* ln_b, float eps, int B, int H, int W, const float* mean3, const float* std3, void* stream) {
+  return stem_fused_src(dtype, 2, x, y, w, bias, ln_w, ln_b, eps, B, H, W, mean3, std3, S(stream));
+}
+int gcv_conv3x3_first_u8(int dtype, const uint8_t* x, void* y, const float* w, const float* b, int stride, int act, int pool,
+                         int B, int H, int W, const float* mean3, const float* std3, void* stream) {
+  return conv3x3_first_src(dtype, 1, x, y, w, b, stride, act, pool, B, H, W, mean3, std3, S(stream));
 }
 int gcv_stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
                    const float* ln_b, float eps, int B, int H, int W, void* stream) {

@@ -329,11 +329,25 @@ __device__ __forceinline__ void c1_mma(float (&d)[4], const uint32_t (&a)[4], ui
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename T, int STRIDE, bool POOL>
+struct C1Norm { float mean[3], sd[3]; };      // U8: Normalize(mean, std) applied to the raw crops
+
+// U8 = false: x = fp32 [B,3,H,W] pre-processed frames.  U8 = true: x = uint8 [B,H,W,3] raw crops; the normalisation
+// (model/pred_func.py:95-108 + dataset/loader.py:63-77) is a 3 x 256 table of T(fdiv(fdiv(u, 255) - mean, std)), the very
+// operand the fp32 path builds from the pre-processed frame, so both paths give bit-identical outputs.
+template <typename T, int STRIDE, bool POOL, bool U8>
 __global__ void __launch_bounds__(256)
-conv3x3_first_mma_kernel(const float* __restrict__ x, T* __restrict__ y, const float* __restrict__ w,
+conv3x3_first_mma_kernel(const void* __restrict__ xin, T* __restrict__ y, const float* __restrict__ w,
                          const float* __restrict__ bias, int act, int B, int H, int W, int Hc, int Wc, int tiles_x,
-                         int tiles_y, int n_tiles) {
+                         int tiles_y, int n_tiles, const C1Norm nrm) {
+  const float* x = reinterpret_cast<const float*>(xin);
+  __shared__ uint16_t s_lut[U8 ? 3 * 256 : 2];
+  if constexpr (U8) {
+    for (int i = threadIdx.x; i < 3 * 256; i += 256) {
+      const int c = i >> 8;
+      const T v = from_f<T>(__fdiv_rn(__fdiv_rn((float)(i & 255), 255.0f) - nrm.mean[c], nrm.sd[c]));
+      s_lut[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+  }
   constexpr int IN_H = C1_ROWS * STRIDE + 2, IN_W = C1_COLS * STRIDE + 2;
   extern __shared__ __align__(16) uint8_t c1sm[];
   uint2* tile = reinterpret_cast<uint2*>(c1sm);                       // [IN_H][IN_W] pixels of 4 x 16 bit (R, G, B, 0)
@@ -369,7 +383,31 @@ conv3x3_first_mma_kernel(const float* __restrict__ x, T* __restrict__ y, const f
     const int ty = r / tiles_x, tx = r - ty * tiles_x;
     const int iy0 = ty * C1_ROWS * STRIDE - 1, ix0 = tx * C1_COLS * STRIDE - 1;
     const float* xb = x + (int64_t)b * 3 * H * W;
-    __syncthreads();                                   // the previous tile's readers are done
+    __syncthreads();                                   // the previous tile's readers are done (first tile: the table is built)
+    if constexpr (U8) {
+      const uint8_t* ub = reinterpret_cast<const uint8_t*>(xin) + (int64_t)b * H * W * 3;
+      for (int i0 = threadIdx.x; i0 < IN_H * IN_W; i0 += 4 * 256) {
+        uint32_t c[4][3];
+        bool oks[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          const int py = i / IN_W, px = i - py * IN_W;
+          const int iy = iy0 + py, ix = ix0 + px;
+          oks[u] = i < IN_H * IN_W && iy >= 0 && iy < H && ix >= 0 && ix < W;
+          const uint8_t* p = ub + ((int64_t)iy * W + ix) * 3;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) c[u][ch] = oks[u] ? (uint32_t)__ldg(p + ch) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          if (i < IN_H * IN_W)                        // zero padding is applied to the NORMALISED image
+            tile[i] = oks[u] ? make_uint2((uint32_t)s_lut[c[u][0]] | ((uint32_t)s_lut[256 + c[u][1]] << 16), (uint32_t)s_lut[512 + c[u][2]])
+                             : make_uint2(0u, 0u);
+        }
+      }
+    } else
     // four pixels per thread and pass: all twelve loads are issued before the first one is consumed
     for (int i0 = threadIdx.x; i0 < IN_H * IN_W; i0 += 4 * 256) {
       float c[4][3];
@@ -459,9 +497,23 @@ conv3x3_first_mma_kernel(const float* __restrict__ x, T* __restrict__ y, const f
 }
 }  // namespace
 
+int conv3x3_first_src(int dtype, int u8, const void* x, void* y, const float* w, const float* b, int stride, int act,
+                      int pool, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t stream);
+
 int conv3x3_first(int dtype, const float* x, void* y, const float* w, const float* b, int stride, int act, int pool,
                   int B, int H, int W, cudaStream_t stream) {
+  return conv3x3_first_src(dtype, 0, x, y, w, b, stride, act, pool, B, H, W, nullptr, nullptr, stream);
+}
+
+// u8 != 0: x is uint8 [B,H,W,3] raw crops, normalised with (mean3, std3) (host pointers) on the fly; 16-bit dtypes only.
+int conv3x3_first_src(int dtype, int u8, const void* xv, void* y, const float* w, const float* b, int stride, int act,
+                      int pool, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t stream) {
+  const float* x = reinterpret_cast<const float*>(xv);
   GCV_REQUIRE((stride == 1 || stride == 2) && B > 0, "conv3x3_first: stride must be 1 or 2");
+  GCV_REQUIRE(!u8 || (mean3 && std3 && (dtype == GCV_BF16 || dtype == GCV_F16)), "conv3x3_first: the uint8 source needs mean / std and a 16-bit dtype");
+  C1Norm nrm{};
+  if (u8)
+    for (int c = 0; c < 3; ++c) { nrm.mean[c] = mean3[c]; nrm.sd[c] = std3[c]; }
   GCV_REQUIRE(!(stride == 2 && pool), "conv3x3_first: stride 2 with pooling is not a reference configuration");
   const int Hc = (H + 2 - 3) / stride + 1, Wc = (W + 2 - 3) / stride + 1;
   const int Ho = pool ? Hc / 2 : Hc, Wo = pool ? Wc / 2 : Wc;
@@ -469,7 +521,8 @@ int conv3x3_first(int dtype, const float* x, void* y, const float* w, const floa
   const unsigned grid = (unsigned)((total + 127) / 128);
   static int mma_env = -1;                      // GCV_CONV1_MMA=0 keeps the fp32 FFMA kernel in the 16-bit modes (A/B timing)
   if (mma_env < 0) { const char* e = getenv("GCV_CONV1_MMA"); mma_env = e ? atoi(e) : 1; }
-  if (mma_env && (dtype == GCV_BF16 || dtype == GCV_F16) && (!pool || (Hc % 2 == 0 && Wc % 2 == 0))) {
+  GCV_REQUIRE(!u8 || !pool || (Hc % 2 == 0 && Wc % 2 == 0), "conv3x3_first: the uint8 source with pooling needs even conv output sizes");
+  if ((mma_env || u8) && (dtype == GCV_BF16 || dtype == GCV_F16) && (!pool || (Hc % 2 == 0 && Wc % 2 == 0))) {
     const int sms = device_sms();
     const int tiles_x = (Wc + C1_COLS - 1) / C1_COLS, tiles_y = (Hc + C1_ROWS - 1) / C1_ROWS;
     const int64_t n_tiles64 = (int64_t)B * tiles_x * tiles_y;
@@ -485,11 +538,17 @@ int conv3x3_first(int dtype, const float* x, void* y, const float* w, const floa
       } else {
         auto go = [&](auto kernel) {
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          kernel<<<g2, 256, smem, stream>>>(x, reinterpret_cast<T*>(y), w, b, act, B, H, W, Hc, Wc, tiles_x, tiles_y, n_tiles);
+          kernel<<<g2, 256, smem, stream>>>(xv, reinterpret_cast<T*>(y), w, b, act, B, H, W, Hc, Wc, tiles_x, tiles_y, n_tiles, nrm);
         };
-        if (stride == 1 && pool) go(conv3x3_first_mma_kernel<T, 1, true>);
-        else if (stride == 1) go(conv3x3_first_mma_kernel<T, 1, false>);
-        else go(conv3x3_first_mma_kernel<T, 2, false>);
+        if (u8) {
+          if (stride == 1 && pool) go(conv3x3_first_mma_kernel<T, 1, true, true>);
+          else if (stride == 1) go(conv3x3_first_mma_kernel<T, 1, false, true>);
+          else go(conv3x3_first_mma_kernel<T, 2, false, true>);
+        } else {
+          if (stride == 1 && pool) go(conv3x3_first_mma_kernel<T, 1, true, false>);
+          else if (stride == 1) go(conv3x3_first_mma_kernel<T, 1, false, false>);
+          else go(conv3x3_first_mma_kernel<T, 2, false, false>);
+        }
         return check_launch("conv3x3_first");
       }
     });

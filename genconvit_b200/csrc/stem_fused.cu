@@ -10,6 +10,9 @@
 //     k-slice is one channel and lane (g, t) needs two adjacent pixels of patch row t/2 (+2): one 8-byte load, 8 tokens
 //     of a row make a contiguous 128-byte segment;
 //   NHWC 16-bit images (the autoencoders' reconstructions): K order (kh, kw, c), a patch row is 24 contiguous bytes.
+//   NHWC uint8 face crops (what model/pred_func.py:95-108 starts from): the Normalize of dataset/loader.py:63-77 is
+//     a 3 x 256 table of (u / 255 - mean) / std rounded to the activation type -- bit for bit the operand the fp32 path
+//     builds from the pre-processed frame -- and the K order is the NCHW path's, so both paths give identical tokens.
 // The LayerNorm is row-local: a token's 96 values live in the 4 lanes of a quad (24 each), exact two-pass statistics
 // with two shuffles per pass.
 #include "common.cuh"
@@ -32,17 +35,31 @@ __device__ __forceinline__ void st_mma(float (&d)[4], const uint32_t (&a)[4], ui
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NCHW: x = fp32 [B,3,H,W], w = [96][(c,kh,kw)] of T.  !NCHW: x = T [B,H,W,3], w = [96][(kh,kw,c)] of T.
-template <typename T, bool NCHW>
+struct StemNorm { float mean[3], sd[3]; };        // SRC 2: Normalize(mean, std) of the uint8 source
+
+// SRC 1: x = fp32 [B,3,H,W], w = [96][(c,kh,kw)] of T.  SRC 0: x = T [B,H,W,3], w = [96][(kh,kw,c)] of T.
+// SRC 2: x = uint8 [B,H,W,3] (raw crops, normalised here), w = [96][(c,kh,kw)] of T.
+template <typename T, int SRC>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __restrict__ w, const float* __restrict__ bias,
                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int B, int H, int W,
-                  int64_t M) {
+                  int64_t M, const StemNorm nrm) {
+  constexpr bool NCHW = SRC == 1;
   __shared__ float s_b[96], s_lw[96], s_lb[96];
+  __shared__ uint16_t s_lut[SRC == 2 ? 3 * 256 : 2];
   for (int i = threadIdx.x; i < 96; i += ST_THREADS) {
     s_b[i] = bias[i];
     s_lw[i] = ln_w[i];
     s_lb[i] = ln_b[i];
+  }
+  if constexpr (SRC == 2) {
+    // the host arithmetic of preprocess_frame, IEEE division and all (gcv_preprocess_frames), then the fp32 -> T
+    // rounding the NCHW path applies to the pre-processed frame
+    for (int i = threadIdx.x; i < 3 * 256; i += ST_THREADS) {
+      const int c = i >> 8;
+      const T v = from_f<T>(__fdiv_rn(__fdiv_rn((float)(i & 255), 255.0f) - nrm.mean[c], nrm.sd[c]));
+      s_lut[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
   }
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   // B fragments: bf[s][nt] = {W[nt*8+g][16s + 2t, +1], W[nt*8+g][16s + 2t+8, +9]}
@@ -61,7 +78,7 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
   const int warps = (int)(gridDim.x * (ST_THREADS / 32));
   // raw operands of a tile: loaded one tile ahead, so that their HBM latency overlaps the previous tile's MMAs,
   // LayerNorm and stores (one CTA of 8 warps per SM: the loads in flight are what feeds the memory system)
-  using Raw = typename std::conditional<NCHW, float2, uint32_t>::type;
+  using Raw = typename std::conditional<NCHW, float2, uint32_t>::type;      // SRC 2: two bytes (pixels kw, kw + 1)
   Raw raw[3][4];
   auto load_raw = [&](int64_t tile) {
 #pragma unroll
@@ -79,6 +96,14 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
         for (int s = 0; s < 3; ++s) {
           raw[s][r] = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W));
           raw[s][r + 2] = __ldg(reinterpret_cast<const float2*>(xb + (int64_t)s * H * W + 2 * (int64_t)W));
+        }
+      } else if constexpr (SRC == 2) {
+        // same K order as NCHW: slice s = channel, lane needs pixels (kh = t/2, kw = 2(t%2), +1) and kh + 2
+        const uint8_t* xb = reinterpret_cast<const uint8_t*>(xin) + ((b * H + 4 * oy + (t >> 1)) * (int64_t)W + 4 * ox + 2 * (t & 1)) * 3;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          raw[s][r] = (uint32_t)__ldg(xb + s) | ((uint32_t)__ldg(xb + 3 + s) << 8);
+          raw[s][r + 2] = (uint32_t)__ldg(xb + 6 * (int64_t)W + s) | ((uint32_t)__ldg(xb + 6 * (int64_t)W + 3 + s) << 8);
         }
       } else {
         // k = kh*12 + kw*3 + c; patch row kh = 12 contiguous elements at pixel (4oy + kh, 4ox)
@@ -102,6 +127,7 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if constexpr (NCHW) a[s][i] = pack2<T>(raw[s][i].x, raw[s][i].y);
+        else if constexpr (SRC == 2) a[s][i] = (uint32_t)s_lut[s * 256 + (raw[s][i] & 255u)] | ((uint32_t)s_lut[s * 256 + (raw[s][i] >> 8)] << 16);
         else a[s][i] = raw[s][i];
       }
     if (tile + warps < tiles) load_raw(tile + warps);
@@ -167,13 +193,16 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
 
 }  // namespace
 
-// y[B*(H/4)*(W/4), 96] = LayerNorm(conv4x4s4(x) + bias).  nchw != 0: x fp32 [B,3,H,W] and w = [96][(c,kh,kw)];
-// nchw == 0: x `dtype` [B,H,W,3] and w = [96][(kh,kw,c)].  16-bit dtypes only.
-int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
-               const float* ln_b, float eps, int B, int H, int W, cudaStream_t stream) {
+// y[B*(H/4)*(W/4), 96] = LayerNorm(conv4x4s4(x) + bias).  src 1 (nchw): x fp32 [B,3,H,W] and w = [96][(c,kh,kw)];
+// src 0: x `dtype` [B,H,W,3] and w = [96][(kh,kw,c)]; src 2: x uint8 [B,H,W,3], normalised with (mean3, std3) (host
+// pointers) on the fly, w = [96][(c,kh,kw)].  16-bit dtypes only.
+int stem_fused_src(int dtype, int src, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
+                   const float* ln_b, float eps, int B, int H, int W, const float* mean3, const float* std3,
+                   cudaStream_t stream) {
   GCV_REQUIRE(dtype == GCV_BF16 || dtype == GCV_F16, "stem_fused: 16-bit dtypes only");
+  GCV_REQUIRE(src >= 0 && src <= 2 && (src != 2 || (mean3 && std3)), "stem_fused: bad source kind %d (uint8 needs mean / std)", src);
   GCV_REQUIRE(B > 0 && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "stem_fused: H, W must be positive multiples of 4");
-  GCV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+  GCV_REQUIRE((src == 2 || (reinterpret_cast<uintptr_t>(x) & 7) == 0) && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(w) & 3) == 0,
               "stem_fused: misaligned pointer");
   const int64_t M = (int64_t)B * (H / 4) * (W / 4);
@@ -181,18 +210,28 @@ int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const
   const int64_t tiles = (M + 15) / 16, per_cta = ST_THREADS / 32;
   const int64_t want = (tiles + per_cta - 1) / per_cta;
   const int grid = (int)(want < sms ? want : sms);   // ~200 registers per thread: one CTA per SM
+  StemNorm nrm{};
+  if (src == 2)
+    for (int c = 0; c < 3; ++c) { nrm.mean[c] = mean3[c]; nrm.sd[c] = std3[c]; }
 #define GCV_STEM_LAUNCH(T, N)                                                                                              \
   stem_fused_kernel<T, N><<<grid, ST_THREADS, 0, stream>>>(x, reinterpret_cast<T*>(y), reinterpret_cast<const T*>(w), bias, \
-                                                           ln_w, ln_b, eps, B, H, W, M)
+                                                           ln_w, ln_b, eps, B, H, W, M, nrm)
   if (dtype == GCV_BF16) {
-    if (nchw) GCV_STEM_LAUNCH(__nv_bfloat16, true);
-    else GCV_STEM_LAUNCH(__nv_bfloat16, false);
+    if (src == 1) GCV_STEM_LAUNCH(__nv_bfloat16, 1);
+    else if (src == 2) GCV_STEM_LAUNCH(__nv_bfloat16, 2);
+    else GCV_STEM_LAUNCH(__nv_bfloat16, 0);
   } else {
-    if (nchw) GCV_STEM_LAUNCH(__half, true);
-    else GCV_STEM_LAUNCH(__half, false);
+    if (src == 1) GCV_STEM_LAUNCH(__half, 1);
+    else if (src == 2) GCV_STEM_LAUNCH(__half, 2);
+    else GCV_STEM_LAUNCH(__half, 0);
   }
 #undef GCV_STEM_LAUNCH
   return check_launch("stem_fused");
+}
+
+int stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, const float* bias, const float* ln_w,
+               const float* ln_b, float eps, int B, int H, int W, cudaStream_t stream) {
+  return stem_fused_src(dtype, nchw ? 1 : 0, x, y, w, bias, ln_w, ln_b, eps, B, H, W, nullptr, nullptr, stream);
 }
 
 }  // namespace gcv

@@ -125,8 +125,12 @@ class PackedConvNeXt:
             x = _empty((m, DIMS[0]), dt, dev)
             r = 0
             for src, nchw, n, hh, ww in a0:
-                L.stem_fused(src, x[r:], self.stem_w_oihw if nchw else self.stem_w, self.stem_b, self.stem_ln[0],
-                             self.stem_ln[1], 1e-6, n, hh, ww, nchw)
+                if isinstance(src, U8Frames):
+                    L.stem_fused_u8(src.t, x[r:], self.stem_w_oihw, self.stem_b, self.stem_ln[0], self.stem_ln[1], 1e-6,
+                                    n, hh, ww, src.mean, src.std)
+                else:
+                    L.stem_fused(src, x[r:], self.stem_w_oihw if nchw else self.stem_w, self.stem_b, self.stem_ln[0],
+                                 self.stem_ln[1], 1e-6, n, hh, ww, nchw)
                 r += n * (hh // 4) * (ww // 4)
         else:
             m = a0.shape[0]
@@ -296,6 +300,29 @@ class PackedSwin:
         return out
 
 
+class U8Frames:
+    """Raw uint8 NHWC face crops [N,H,W,3] on the GPU plus the Normalize(mean, std) the reference applies on the host
+    (model/pred_func.py:95-108, dataset/loader.py:63-77).  Accepted wherever the engine takes the pre-processed fp32 NCHW
+    frames (16-bit modes): the first-touch kernels (encoder conv 1, ConvNeXt stem) read the bytes and normalise in
+    registers -- bit-identical to preprocessing first -- so the fp32 frames never exist."""
+
+    def __init__(self, t, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3 or not t.is_contiguous():
+            raise ValueError(f"U8Frames takes a contiguous uint8 [N,H,W,3] tensor, got {t.dtype} {tuple(t.shape)}")
+        self.t, self.mean, self.std = t, tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        self.shape = (t.shape[0], 3, t.shape[1], t.shape[2])       # the NCHW shape of the frames it stands for
+        self.device, self.is_cuda = t.device, t.is_cuda
+
+
+def _first_conv(x, y, w, b, stride, act, pool, n, hh, ww, dt):
+    if isinstance(x, U8Frames):
+        if dt == torch.float32:
+            raise ValueError("uint8 frames are consumed by the 16-bit kernels; pre-process them for the fp32 mode")
+        L.conv3x3_first_u8(x.t, y, w, b, stride, act, pool, n, hh, ww, x.mean, x.std)
+    else:
+        L.conv3x3_first(x, y, w, b, stride, act, pool, n, hh, ww)
+
+
 def _pack_conv3x3(w, dev, dt):
     """[Co,Ci,3,3] -> [Co, (kh,kw,ci)] matching gcv_im2col3x3's column order."""
     return _cd(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1), dev, dt)
@@ -365,7 +392,7 @@ class PackedED:
         n, _, hh, ww = x.shape
         h, w, c = hh // 2, ww // 2, 16
         e = _empty((n * h * w, c), dt, dev)
-        L.conv3x3_first(x, e, self.enc0_w, self.enc0_b, 1, L.ACT_RELU, True, n, hh, ww)
+        _first_conv(x, e, self.enc0_w, self.enc0_b, 1, L.ACT_RELU, True, n, hh, ww, dt)
         for wt, bias in self.enc:
             co = wt.shape[0]
             if (c, co) == (16, 32) and dt != torch.float32 and h % 2 == 0 and w % 2 == 0:
@@ -416,6 +443,8 @@ class PackedED:
         th, tw = hh // 4, ww // 4
         if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO and self.backbone.dims[0] == 96:
             a0 = [(dec, False, n, hh, ww), (x, True, n, hh, ww)]
+        elif isinstance(x, U8Frames):
+            raise ValueError("uint8 frames need the 16-bit fused stem (convnext_tiny, bf16 / fp16)")
         else:
             a0 = _empty((2 * n * th * tw, 48), dt, dev)
             L.stem_patchify_nhwc(dec, a0, n, hh, ww)
@@ -468,7 +497,7 @@ class PackedVAE:
         n, _, hh, ww = x.shape
         h, w, c = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1, 16
         e = _empty((n * h * w, c), dt, dev)
-        L.conv3x3_first(x, e, self.enc0_w, self.enc0_b, 2, L.ACT_LEAKY, False, n, hh, ww)
+        _first_conv(x, e, self.enc0_w, self.enc0_b, 2, L.ACT_LEAKY, False, n, hh, ww, dt)
         for wt, bias in self.enc:
             co = wt.shape[0]
             h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
@@ -539,6 +568,8 @@ class PackedVAE:
         m1 = n * t1[0] * t1[1]
         if FUSED_STEM and dt != torch.float32 and backend == L.GEMM_AUTO and self.backbone.dims[0] == 96:
             a0 = [(x, True, n, hh, ww), (xhat, False, n, h2, w2)]
+        elif isinstance(x, U8Frames):
+            raise ValueError("uint8 frames need the 16-bit fused stem (convnext_tiny, bf16 / fp16)")
         else:
             a0 = _empty((m1 + n * t2[0] * t2[1], 48), dt, dev)
             L.stem_patchify_nchw(x, a0, n, hh, ww)

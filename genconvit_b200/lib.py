@@ -24,7 +24,7 @@ DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 EXPORTS = [
     "gcv_abi_version", "gcv_last_error", "gcv_device_supported", "gcv_gemm", "gcv_mlp_fused_supported", "gcv_mlp_fused", "gcv_mlp_fused_ln", "gcv_dwconv7_ln", "gcv_dwconv7_stats", "gcv_ln_patchify2",
     "gcv_stem_patchify_nchw", "gcv_stem_patchify_nhwc", "gcv_layernorm_rows", "gcv_pool_ln", "gcv_conv3x3_first",
-    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_convt2x2_mma", "gcv_conv3x3_tc_supported", "gcv_conv3x3_tc", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
+    "gcv_im2col3x3", "gcv_maxpool2", "gcv_conv3x3_c16", "gcv_conv3x3_c32", "gcv_stem_fused", "gcv_stem_fused_u8", "gcv_conv3x3_first_u8", "gcv_ln_finalize", "gcv_convt2x2_small", "gcv_convt2x2_mma", "gcv_conv3x3_tc_supported", "gcv_conv3x3_tc", "gcv_resize2x_to_nchw", "gcv_nhwc_to_nchw_f32", "gcv_score_videos", "gcv_score_videos_pair",
     "gcv_swin_window_attention", "gcv_swin_patch_merge", "gcv_mean_tokens", "gcv_preprocess_frames",
 ]
 
@@ -76,6 +76,8 @@ def load():
     lib.gcv_maxpool2.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.gcv_ln_finalize.argtypes = [vp, vp, i64, i32, i32, f32, vp]
     lib.gcv_stem_fused.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp]
+    lib.gcv_stem_fused_u8.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp]
+    lib.gcv_conv3x3_first_u8.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.gcv_conv3x3_c32.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_conv3x3_c16.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.gcv_convt2x2_small.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -304,6 +306,25 @@ def conv3x3_first(x, y, w, b, stride, act, pool, B, H, W):
     assert x.dtype == torch.float32
     _run("conv3x3_first", B * H * W * 3.0 * 4 + y.numel() * y.element_size(), lambda: load().gcv_conv3x3_first(
         DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(b), stride, act, 1 if pool else 0, B, H, W, _stream()))
+
+
+def conv3x3_first_u8(x, y, w, b, stride, act, pool, B, H, W, mean, std):
+    """The first encoder conv straight from raw uint8 NHWC crops (normalised in the kernel); see gcv_conv3x3_first_u8."""
+    assert x.dtype == torch.uint8
+    _need(x, B * H * W * 3, "conv3x3_first_u8 x")
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _run("conv3x3_first", B * H * W * 3.0 + y.numel() * y.element_size(), lambda: load().gcv_conv3x3_first_u8(
+        DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(b), stride, act, 1 if pool else 0, B, H, W, m3, s3, _stream()), "u8")
+
+
+def stem_fused_u8(x, y, w, bias, ln_w, ln_b, eps, B, H, W, mean, std):
+    """The ConvNeXt stem straight from raw uint8 NHWC crops (normalised in the kernel); see gcv_stem_fused_u8."""
+    assert x.dtype == torch.uint8
+    _need(x, B * H * W * 3, "stem_fused_u8 x")
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    _run("stem_fused", B * H * W * 3.0 + B * (H // 4) * (W // 4) * 96.0 * y.element_size(),
+         lambda: load().gcv_stem_fused_u8(DTYPE_CODE[y.dtype], _p(x), _p(y), _p(w), _p(bias), _p(ln_w), _p(ln_b), eps, B, H, W,
+                                          m3, s3, _stream()), f"B{B} H{H} u8")
 
 
 def im2col3x3(x, a, B, H, W, Cc, stride):

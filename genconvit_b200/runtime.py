@@ -27,9 +27,11 @@ class VideoScorer:
         the reference (genconvit_vae.py:46); or a fixed [batch_frames,12544] tensor.
 
         ``submit`` takes either the reference's pre-processed frames (fp32 NCHW, model/pred_func.py:95-108) or the raw
-        uint8 NHWC face crops that function starts from; the latter cross PCIe at a quarter of the bytes and are
-        normalised on the GPU (``gcv_preprocess_frames``, bit-identical to the host arithmetic) straight into the
-        graph's input buffer."""
+        uint8 NHWC face crops that function starts from.  The latter cross PCIe at a quarter of the bytes and are never
+        expanded: the first kernels of both networks (encoder conv 1, ConvNeXt stem) read the bytes and normalise in
+        registers, bit-identically to the host arithmetic.  The graph input is double-buffered -- one captured graph per
+        uint8 buffer, sharing one memory pool -- so batch k+1's copy lands while batch k computes, with no staging copy.
+        (fp32 compute mode: the uint8 frames go through ``gcv_preprocess_frames`` into the fp32 input buffer.)"""
         if batch_frames % frames_per_video:
             raise ValueError("batch_frames must hold whole videos")
         self.model = model
@@ -52,15 +54,20 @@ class VideoScorer:
         self.ev_stage_free = torch.cuda.Event()
         self.ev_u8_free = [torch.cuda.Event(), torch.cuda.Event()]
         self.graph = None
+        self.u8_graph = [None, None]         # one captured step per uint8 input buffer (16-bit modes)
+        self.use_graph = use_graph
+        from .modules import compute_dtype_of
+        first = model.model_ed if model.net != "vae" else model.model_vae
+        self.u8_fused = compute_dtype_of(first, getattr(first, "compute_dtype", None)) != torch.float32
         self.launches_per_step = 0
         self.out = None                      # [2, V] fp32 on device: row 0 = class, row 1 = score
         self._prepare(use_graph)
 
     # -- one step worth of kernels (eager or under capture) --
-    def _step(self):
+    def _step(self, frames=None):
         if self.has_vae and not self.fixed_eps:
             self.eps.normal_()
-        x1, x2 = self.model.forward_parts(self.x_static, self.eps)
+        x1, x2 = self.model.forward_parts(self.x_static if frames is None else frames, self.eps)
         if self.out is None:
             self.out = torch.empty((2, self.n_videos), dtype=torch.float32, device=self.dev)   # row 0 class, row 1 score
         # fused scoring straight from the two logit buffers: no torch.cat, no per-row copies -- the step launches only
@@ -93,6 +100,30 @@ class VideoScorer:
             else:
                 self._step()
 
+    def _run_u8(self, i):
+        """One step straight from uint8 buffer ``i`` (captured on first use; the second graph shares the first one's pool:
+        the two never run at the same time)."""
+        with torch.no_grad():
+            frames = engine.U8Frames(self.u8_stage[i], _MEAN, _STD)
+            if not self.use_graph:
+                self._step(frames)
+                return
+            if self.u8_graph[i] is None:
+                cur = torch.cuda.current_stream(self.dev)
+                s = torch.cuda.Stream(device=self.dev)
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    self._step(frames)       # eager once: the results of this very batch, and a warm allocator
+                cur.wait_stream(s)
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                other = self.u8_graph[i ^ 1] or self.graph
+                with torch.cuda.graph(g, pool=other.pool() if other is not None else None):
+                    self._step(frames)
+                self.u8_graph[i] = g
+                return                       # the eager run above already produced this batch's scores
+            self.u8_graph[i].replay()
+
     def submit(self, frames_host, out_host):
         """Enqueue one batch: pinned-host frames -> device, forward + scoring, results -> pinned host.
         Asynchronous; overlaps this batch's H2D with the previous batch's compute.
@@ -109,10 +140,15 @@ class VideoScorer:
                 self.u8_stage[i] = torch.empty((self.n, self.img, self.img, 3), dtype=torch.uint8, device=self.dev)
                 self.ev_u8_free[i].record(cur)
             with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(self.ev_u8_free[i])          # the preprocess kernel that last read it is done
+                self.copy_stream.wait_event(self.ev_u8_free[i])          # the step that last read this buffer is done
                 self.u8_stage[i].copy_(frames_host, non_blocking=True)
                 self.ev_h2d.record(self.copy_stream)
             cur.wait_event(self.ev_h2d)
+            if self.u8_fused:
+                self._run_u8(i)
+                self.ev_u8_free[i].record(cur)
+                out_host.copy_(self.out, non_blocking=True)
+                return
             with torch.cuda.device(self.dev):
                 L.preprocess_frames(self.u8_stage[i], self.x_static, self.n, self.img, self.img, _MEAN, _STD)
             self.ev_u8_free[i].record(cur)

@@ -146,6 +146,17 @@ int gcv_stem_fused(int dtype, int nchw, const void* x, void* y, const void* w, c
                    const float* ln_b, float eps, int B, int H, int W, void* stream);
 int gcv_stem_patchify_nchw(int dtype, const float* x, void* a, int B, int H, int W, void* stream);
 int gcv_stem_patchify_nhwc(int dtype, const void* x, void* a, int B, int H, int W, void* stream);
+/* gcv_stem_fused_u8 / gcv_conv3x3_first_u8: the same two first-touch kernels reading the RAW uint8 face crops
+ *   x [B,H,W,3] (what model/pred_func.py:95-108 preprocess_frame starts from) and applying its
+ *   (x / 255 - mean) / std (dataset/loader.py:63-77; mean3 / std3: host pointers to 3 floats) on the fly, as a
+ *   3 x 256 table holding exactly the 16-bit operand the fp32 entry points build from the pre-processed frame:
+ *   outputs are bit-identical to gcv_preprocess_frames followed by gcv_stem_fused(nchw = 1) / gcv_conv3x3_first.
+ *   gcv_stem_fused_u8 takes w = [96][(c,kh,kw)] like the nchw form.  bf16/fp16 only. */
+int gcv_stem_fused_u8(int dtype, const uint8_t* x, void* y, const void* w, const float* bias, const float* ln_w,
+                      const float* ln_b, float eps, int B, int H, int W, const float* mean3, const float* std3,
+                      void* stream);
+int gcv_conv3x3_first_u8(int dtype, const uint8_t* x, void* y, const float* w, const float* b, int stride, int act,
+                         int pool, int B, int H, int W, const float* mean3, const float* std3, void* stream);
 int gcv_layernorm_rows(int dtype, const void* x, void* y, const float* w, const float* b, float eps,
                        int64_t rows, int C, void* stream);
 int gcv_pool_ln(int dtype, const void* x, void* y, const float* w, const float* b, float eps,

@@ -4,6 +4,8 @@ import os
 import torch
 import torch.nn as nn
 
+from genconvit_b200 import engine as _engine_mod
+
 from .genconvit_ed import GenConViTED
 from .genconvit_vae import GenConViTVAE
 
@@ -99,7 +101,11 @@ class GenConViT(nn.Module):
 
     def forward_parts(self, x, eps=None):
         """The two networks' fp32 logits (ED [N,2] | None, VAE [N,2] | None) without the reference's concatenation:
-        the bulk runtime scores straight from both buffers (gcv_score_videos_pair).  ``x``: fp32 NCHW on the GPU."""
+        the bulk runtime scores straight from both buffers (gcv_score_videos_pair).  ``x``: the pre-processed fp32 NCHW
+        frames on the GPU, or the raw uint8 NHWC face crops (tensor or ``engine.U8Frames``; 16-bit modes): the first
+        kernels of both networks then apply ``preprocess_frame``'s normalisation themselves, bit-identically."""
+        if torch.is_tensor(x) and x.dtype == torch.uint8:
+            x = _engine_mod.U8Frames(x)
         x1 = x2 = None
         two = self.net not in ("ed", "vae")
         if two and _TWO_STREAMS:

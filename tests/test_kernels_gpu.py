@@ -689,3 +689,35 @@ def test_conv3x3_tc_rejects_unsupported():
     w, b = torch.zeros(128, 576, device=DEV, dtype=torch.float16), torch.zeros(128, device=DEV)
     with pytest.raises(L.GcvError):                    # pooling needs even conv output sizes
         L.conv3x3_tc(x, torch.zeros(1, 3, 3, 128, device=DEV, dtype=torch.float16), w, b, 1, L.ACT_RELU, True, 1, 7, 7, 64, 128)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_uint8_first_touch_kernels_equal_preprocess_then_fp32_kernels(dtype):
+    """gcv_conv3x3_first_u8 / gcv_stem_fused_u8 on raw uint8 NHWC crops == gcv_preprocess_frames followed by the fp32-input
+    kernels, bit for bit (reference model/pred_func.py:95-108 then genconvit_ed.py:15-16 / genconvit_vae.py:16-18 /
+    the ConvNeXt stem): same operand bits, same K order."""
+    L = _lib()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    B, H, W = 3, 64, 96
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(DEV)
+    u8[0, :2] = 0
+    u8[0, 2:4] = 255
+    x = torch.empty((B, 3, H, W), device=DEV)
+    L.preprocess_frames(u8, x, B, H, W, mean, std)
+    w1, b1 = _rand(16, 3, 3, 3, seed=2, scale=0.2), _rand(16, seed=3, scale=0.1)
+    for stride, act, pool in ((1, L.ACT_RELU, True), (2, L.ACT_LEAKY, False), (1, L.ACT_RELU, False)):
+        ho, wo = ((H - 1) // stride + 1) // (2 if pool else 1), ((W - 1) // stride + 1) // (2 if pool else 1)
+        a = torch.full((B, ho, wo, 16), float("nan"), device=DEV, dtype=dtype)
+        b = torch.full_like(a, float("nan"))
+        L.conv3x3_first(x, a, w1, b1, stride, act, pool, B, H, W)
+        L.conv3x3_first_u8(u8, b, w1, b1, stride, act, pool, B, H, W, mean, std)
+        assert torch.equal(a, b), (stride, pool)
+    ws = _rand(96, 3, 4, 4, seed=4, scale=0.15).reshape(96, 48).to(dtype).contiguous()
+    bs, lw, lb = _rand(96, seed=5, scale=0.1), _rand(96, seed=6).abs() + 0.5, _rand(96, seed=7, scale=0.2)
+    M = B * (H // 4) * (W // 4)
+    a = torch.full((M, 96), float("nan"), device=DEV, dtype=dtype)
+    b = torch.full_like(a, float("nan"))
+    L.stem_fused(x, a, ws, bs, lw, lb, 1e-6, B, H, W, True)
+    L.stem_fused_u8(u8, b, ws, bs, lw, lb, 1e-6, B, H, W, mean, std)
+    assert torch.equal(a, b)

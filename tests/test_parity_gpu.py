@@ -405,24 +405,62 @@ def test_forward_parts_and_pair_scoring_match_the_concatenated_path(full_model):
 
 def test_video_scorer_uint8_ingest_matches_preprocess_then_forward(full_model):
     """VideoScorer.submit with raw uint8 NHWC crops == model.pred_func.preprocess_frame (reference :95-108) followed by
-    the forward: same classes, same scores bit for bit (the GPU normalisation is bit-identical to the host arithmetic)."""
+    the forward: same classes, same scores bit for bit.  The uint8 bytes feed the first kernels of both networks
+    directly (gcv_conv3x3_first_u8 / gcv_stem_fused_u8; the table they normalise with holds the host arithmetic's
+    values); five batches go through both double-buffered graph inputs: eager first use, capture, replays."""
     import numpy as np
     from genconvit_b200.runtime import VideoScorer
     from model import pred_func
     from oracle.weights import synthetic_eps
     n, fpv = 32, 16
     rng = np.random.default_rng(5)
-    frames = rng.integers(0, 256, size=(n, 224, 224, 3), dtype=np.uint8)
     eps = synthetic_eps(n, 151).to(DEV)
     full_model.set_compute_dtype("fp16")
     sc = VideoScorer(full_model, n, fpv, eps=eps, use_graph=True)
-    cls, val = sc.score(torch.from_numpy(frames).pin_memory())
-    full_model.model_vae.set_epsilon(eps)
-    try:
-        c2, v2 = pred_func.pred_videos(pred_func.preprocess_frame(frames), full_model, fpv)
-    finally:
-        full_model.model_vae.set_epsilon(None)
-    assert torch.equal(cls, c2) and torch.equal(val, v2)
+    assert sc.u8_fused
+    for k in range(5):
+        frames = rng.integers(0, 256, size=(n, 224, 224, 3), dtype=np.uint8)
+        if k == 3:
+            frames[:] = 0                                   # extreme table entries
+            frames[1::2] = 255
+        before = L_launches()
+        cls, val = sc.score(torch.from_numpy(frames).pin_memory())
+        if k >= 2:
+            assert L_launches() == before                   # replays: no eager launch, no preprocess kernel
+        full_model.model_vae.set_epsilon(eps)
+        try:
+            c2, v2 = pred_func.pred_videos(pred_func.preprocess_frame(frames), full_model, fpv)
+        finally:
+            full_model.model_vae.set_epsilon(None)
+        assert torch.equal(cls, c2) and torch.equal(val, v2), k
+
+
+def L_launches():
+    from genconvit_b200 import lib
+    return lib.launches
+
+
+def test_uint8_frames_through_the_module_api(full_model):
+    """model.forward_parts(uint8 NHWC) == forward_parts(preprocess_frame(...)) bit for bit in both 16-bit modes; the fp32
+    mode refuses (its kernels read the pre-processed frames)."""
+    import numpy as np
+    from model import pred_func
+    from oracle.weights import synthetic_eps
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, size=(6, 224, 224, 3), dtype=np.uint8)
+    eps = synthetic_eps(6, 171).to(DEV)
+    u8 = torch.from_numpy(frames).to(DEV)
+    x = pred_func.preprocess_frame(frames).to(DEV)
+    with torch.no_grad():
+        for mode in ("bf16", "fp16"):
+            full_model.set_compute_dtype(mode)
+            a1, a2 = full_model.forward_parts(u8, eps)
+            b1, b2 = full_model.forward_parts(x, eps)
+            assert torch.equal(a1, b1) and torch.equal(a2, b2), mode
+        full_model.set_compute_dtype("fp32")
+        with pytest.raises(ValueError):
+            full_model.forward_parts(u8, eps)
+    full_model.set_compute_dtype("fp16")
 
 
 def test_offload_unused_parameters_keeps_the_logits(full_model):
