@@ -28,13 +28,16 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                       // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter: TLP hides tcgen05.ld / MUFU / smem latency
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStatWarp = 2 + kEpiWarps;       // MODE 3: two warps reduce the tile rows' LayerNorm partial sums one tile ahead
+constexpr int kStatWarps = 2;                 // (640 threads leave exactly the 96 registers per thread the epilogues need)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * kStatWarps;
+constexpr int kStatStages = 4;                // ring of per-tile row statistics, indexed like the accumulator stages
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccStages = 8;              // TMEM accumulator ring: 512 columns / block_n
 constexpr int kTileSmem = 160 * 1024;            // 227 KB budget minus control block, epilogue staging, vectors, slack
 constexpr int kVecMaxN = 3072;                   // bias / layer-scale vectors up to this N are staged in smem
 constexpr int kVecSmem = 2 * kVecMaxN * 4;
-constexpr int kCtrlSmem = 1024;
+constexpr int kCtrlSmem = 1024 + kStatStages * 128 * 8;   // barriers + TMEM slot (1 KB), row-statistics ring (4 KB)
 constexpr int kStageRow = 64;                            // staged row: 32 x 16-bit, 16-byte pieces XOR-swizzled (TMA SWIZZLE_64B)
 constexpr int kStageWarp = 32 * kStageRow;               // per epilogue warp: 32 rows x 32 columns = one TMA store box
 constexpr int kStageSmem = kEpiWarps * kStageWarp;
@@ -100,6 +103,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + kMaxAccStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + kMaxAccStages);
+  uint64_t* stat_full = reinterpret_cast<uint64_t*>(smem_raw + 512);      // MODE 3 with partial sums (ep.ln_chunks > 0)
+  uint64_t* stat_empty = stat_full + kStatStages;
+  float2* stat_ring = reinterpret_cast<float2*>(smem_raw + 1024);         // [kStatStages][BM] (rstd, -mean * rstd)
   uint8_t* stage_base = smem_raw + kCtrlSmem;            // epilogue staging, kStageWarp bytes per warp
   float* vec_bias = reinterpret_cast<float*>(smem_raw + kCtrlSmem + kStageSmem);   // [kVecMaxN] bias, then gamma
   float* vec_gamma = vec_bias + kVecMaxN;
@@ -117,6 +123,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(smem_u32(full_bar + s), 1);
       mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    for (int s = 0; s < kStatStages; ++s) {
+      mbar_init(smem_u32(stat_full + s), kStatWarps);
+      mbar_init(smem_u32(stat_empty + s), kEpiWarps);
     }
     for (int s = 0; s < p.acc_stages; ++s) {
       mbar_init(smem_u32(tmem_full + s), 1);
@@ -253,6 +263,81 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp >= kStatWarp) {
+    // ===================== row statistics (folded LayerNorm from per-chunk partial sums) =====================
+    // One tile ahead of the epilogue: (rstd, -mean * rstd) of the tile's 128 rows (64 per warp, two per lane), summed in
+    // chunk order (the values gcv_ln_finalize writes), into the ring slot of the tile's accumulator stage.  The partial
+    // sums are 8 * chunks bytes per row, read once per tile from L2 here instead of by every epilogue thread -- and the
+    // 24 reduction launches per step between the depthwise convolutions and the fc1 GEMMs are gone.  All of a lane's
+    // loads are in flight together: one L2 round trip per tile (two for 24 chunks), well inside a tile period.
+    if constexpr (MODE == 3) {
+      const int chunks = p.ep.ln_chunks;
+      if (chunks > 0) {
+        const int sw = warp - kStatWarp;
+        const float inv = 1.0f / (float)p.K;
+        const float eps_ln = p.ep.ln_eps;
+        auto finish = [&](float sum, float sq) {
+          const float mean = sum * inv;
+          const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv), 0.0f) + eps_ln);
+          return make_float2(rstd, -mean * rstd);
+        };
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = walker; tile < walk_tiles; tile += walkers) {
+          const int mw = tile / p.tiles_n;
+          const int r0 = sw * 64 + lane, r1 = r0 + 32;                     // this lane's two rows of the tile
+          const int64_t m0 = (int64_t)(DUO ? 2 * mw + (int)crank : mw) * BM + r0, m1 = m0 + 32;
+          mbar_wait(smem_u32(stat_empty + as), aphase ^ 1);
+          float2 rs0 = make_float2(1.0f, 0.0f), rs1 = rs0;
+          if ((chunks & 1) == 0 && chunks <= 12) {
+            const int nv = chunks >> 1;
+            const float4* s0 = reinterpret_cast<const float4*>(p.ep.ln_stats) + (m0 < p.M ? m0 : 0) * nv;
+            const float4* s1 = reinterpret_cast<const float4*>(p.ep.ln_stats) + (m1 < p.M ? m1 : 0) * nv;
+            float4 v0[6], v1[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              v0[c] = c < nv ? __ldg(s0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v1[c] = c < nv ? __ldg(s1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float a = 0.0f, b = 0.0f, c2 = 0.0f, d = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+              if (c < nv) {
+                a += v0[c].x; b += v0[c].y; a += v0[c].z; b += v0[c].w;
+                c2 += v1[c].x; d += v1[c].y; c2 += v1[c].z; d += v1[c].w;
+              }
+            rs0 = finish(a, b);
+            rs1 = finish(c2, d);
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+              const int64_t m = i ? m1 : m0;
+              float sum = 0.0f, sq = 0.0f;
+              if (m < p.M) {
+                if ((chunks & 1) == 0 && chunks <= 24) {
+                  const float4* src = reinterpret_cast<const float4*>(p.ep.ln_stats) + m * (chunks >> 1);
+                  float4 v[12];
+#pragma unroll
+                  for (int c = 0; c < 12; ++c) v[c] = c < (chunks >> 1) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int c = 0; c < 12; ++c)
+                    if (c < (chunks >> 1)) { sum += v[c].x; sq += v[c].y; sum += v[c].z; sq += v[c].w; }
+                } else {
+                  const float2* src = reinterpret_cast<const float2*>(p.ep.ln_stats) + m * chunks;
+                  for (int c = 0; c < chunks; ++c) { const float2 v = __ldg(src + c); sum += v.x; sq += v.y; }
+                }
+              }
+              (i ? rs1 : rs0) = finish(sum, sq);
+            }
+          }
+          stat_ring[as * BM + r0] = rs0;
+          stat_ring[as * BM + r1] = rs1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(stat_full + as));
+          if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
   } else {
     // ===================== epilogue =====================
     // Phase A (thread = accumulator row): tcgen05.ld 32 columns, bias / activation / layer-scale /
@@ -282,8 +367,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int64_t m_warp = (int64_t)m_blk * BM + quarter * 32;
       const int64_t m = m_warp + lane;
       float2 lnrs = make_float2(1.0f, 0.0f);             // folded LayerNorm: (rstd, -mean * rstd) of this thread's row,
-      if constexpr (MODE == 3) {                         // fetched before blocking on the accumulator
-        if (m < p.M && sub < chunks) lnrs = ln_row_scale(ep.ln_stats, m, ep.ln_chunks, p.K, ep.ln_eps);
+      if constexpr (MODE == 3) {
+        if (ep.ln_chunks > 0) {                          // reduced by the statistics warp while the previous tile drained
+          mbar_wait(smem_u32(stat_full + as), aphase);
+          lnrs = stat_ring[as * BM + quarter * 32 + lane];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(stat_empty + as));
+        } else if (m < p.M && sub < chunks) {            // one pair per row (gcv_ln_finalize), fetched before blocking
+          lnrs = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + m);
+        }
         lnrs.x *= 0.5f; lnrs.y *= 0.5f;                  // GELU is evaluated from x / 2 (ln_bias_gelu_pack8)
       }
       uint4 res[4];                                      // MODE 4: residual of this thread's row, 32 columns of a chunk
@@ -615,6 +707,7 @@ int gemm_tcgen05(int dtype, const void* A, int64_t lda, const void* B, int64_t l
   const int stage_bytes = BM * BK * 2 + (duo ? p.block_n / 2 : p.block_n) * BK * 2;
   p.acc_stages = 512 / p.block_n;
   if (p.acc_stages > kMaxAccStages) p.acc_stages = kMaxAccStages;
+  if (ep->ln_stats && ep->ln_chunks > 0 && p.acc_stages > kStatStages) p.acc_stages = kStatStages;   // one statistics slot per stage
   p.num_stages = kTileSmem / stage_bytes;
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   {

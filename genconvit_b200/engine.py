@@ -29,6 +29,9 @@ LN_FOLD = os.environ.get("GCV_NO_LNFOLD", "0") != "1"
 # 16-bit modes: the stem (4x4 patchify + conv + LayerNorm2d) as ONE tensor-core kernel reading the frames directly.
 # GCV_NO_FUSED_STEM=1 keeps im2col + GEMM + row LayerNorm (A/B timing).
 FUSED_STEM = os.environ.get("GCV_NO_FUSED_STEM", "0") != "1"
+# GCV_LN_FINALIZE=1: reduce the LayerNorm partial sums of stages 2-3 with a separate gcv_ln_finalize launch per block
+# instead of inside the fc1 GEMM (its statistics warps); A/B timing only
+LN_FINALIZE = os.environ.get("GCV_LN_FINALIZE", "0") == "1"
 
 
 def _on_device(fn):
@@ -160,7 +163,6 @@ class PackedConvNeXt:
                                                                                     L.mlp_fused_supported(dt, c))
             stats = _empty((m, c // 32, 2), torch.float32, dev) if fold else None
             hid = None if fused else _empty((m, 4 * c), dt, dev)
-            rowstat = _empty((m, 2), torch.float32, dev) if (fold and not fused) else None
             for blk in st["blocks"]:
                 r = 0
                 for b, h, w in segs:
@@ -175,10 +177,15 @@ class PackedConvNeXt:
                 elif fused:
                     L.mlp_fused(y, blk["fc1_w"], blk["fc1_b"], blk["fc2_w"], blk["fc2_b"], blk["gamma"], x, m, c)
                 else:
-                    if fold:
-                        # partial sums -> one (rstd, -mean*rstd) pair per row, once, not in every epilogue thread
+                    if fold and LN_FINALIZE:
+                        # partial sums -> one (rstd, -mean*rstd) pair per row by a separate launch (A/B timing)
+                        rowstat = _empty((m, 2), torch.float32, dev)
                         L.ln_finalize(stats, rowstat, m, c, 1e-6)
                         L.gemm(y, blk["fc1_wf"], hid, m, 4 * c, c, bias=blk["fc1_bf"], act=L.ACT_GELU, ln_stats=rowstat,
+                               ln_colsum=blk["fc1_cs"], ln_eps=1e-6, backend=backend)
+                    elif fold:
+                        # the GEMM's statistics warps reduce the partial sums to (rstd, -mean*rstd) per row, a tile ahead
+                        L.gemm(y, blk["fc1_wf"], hid, m, 4 * c, c, bias=blk["fc1_bf"], act=L.ACT_GELU, ln_stats=stats,
                                ln_colsum=blk["fc1_cs"], ln_eps=1e-6, backend=backend)
                     else:
                         L.gemm(y, blk["fc1_w"], hid, m, 4 * c, c, bias=blk["fc1_b"], act=L.ACT_GELU, backend=backend)

@@ -313,7 +313,8 @@ def test_dwconv7_stats(cfg, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape", [(1000, 384, 96), (4096 + 13, 1536, 384), (300, 3072, 768), (128 * 148 * 2 + 5, 768, 192)])
+@pytest.mark.parametrize("shape", [(1000, 384, 96), (4096 + 13, 1536, 384), (300, 3072, 768), (128 * 148 * 2 + 5, 768, 192),
+                                   (128 * 148 * 3 + 50, 64, 64), (128 * 148 * 5 + 1, 128, 128)])
 def test_gemm_folded_layernorm(shape, dtype):
     """fc1(LayerNorm(v)) computed as GELU(rstd * (v W'^T - mean * colsum) + b') from per-chunk partial sums."""
     L = _lib()
@@ -338,6 +339,8 @@ def test_gemm_folded_layernorm(shape, dtype):
     d1 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
     L.gemm(v, w1f, d1, M, N, K, bias=b1f, act=L.ACT_GELU, ln_stats=rowstat, ln_colsum=cs, ln_eps=1e-6)
     _close(d1, want, TOL[dtype], f"folded LN gemm, finalised stats {shape}")
+    # the GEMM's statistics warp reduces the partial sums in the same order as ln_finalize: identical outputs
+    assert torch.equal(d, d1)
     # the SIMT back end implements the same epilogue
     if M <= 1000:
         d2 = torch.full((M, N), float("nan"), device=DEV, dtype=dtype)
