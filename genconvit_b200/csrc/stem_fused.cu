@@ -46,7 +46,9 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
                   int64_t M, const StemNorm nrm) {
   constexpr bool NCHW = SRC == 1;
   __shared__ float s_b[96], s_lw[96], s_lb[96];
-  __shared__ uint16_t s_lut[SRC == 2 ? 3 * 256 : 2];
+  // SRC 2: table[c][u][lane] as 32-bit words (dynamic shared memory, 96 KB): lane l only ever reads bank l, so the 24
+  // look-ups a lane makes per tile are conflict-free whatever the pixel values are
+  extern __shared__ uint32_t s_lut[];
   for (int i = threadIdx.x; i < 96; i += ST_THREADS) {
     s_b[i] = bias[i];
     s_lw[i] = ln_w[i];
@@ -55,9 +57,9 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
   if constexpr (SRC == 2) {
     // the host arithmetic of preprocess_frame, IEEE division and all (gcv_preprocess_frames), then the fp32 -> T
     // rounding the NCHW path applies to the pre-processed frame
-    for (int i = threadIdx.x; i < 3 * 256; i += ST_THREADS) {
-      const int c = i >> 8;
-      const T v = from_f<T>(__fdiv_rn(__fdiv_rn((float)(i & 255), 255.0f) - nrm.mean[c], nrm.sd[c]));
+    for (int i = threadIdx.x; i < 3 * 256 * 32; i += ST_THREADS) {
+      const int c = i >> 13, u = (i >> 5) & 255;
+      const T v = from_f<T>(__fdiv_rn(__fdiv_rn((float)u, 255.0f) - nrm.mean[c], nrm.sd[c]));
       s_lut[i] = *reinterpret_cast<const uint16_t*>(&v);
     }
   }
@@ -78,7 +80,7 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
   const int warps = (int)(gridDim.x * (ST_THREADS / 32));
   // raw operands of a tile: loaded one tile ahead, so that their HBM latency overlaps the previous tile's MMAs,
   // LayerNorm and stores (one CTA of 8 warps per SM: the loads in flight are what feeds the memory system)
-  using Raw = typename std::conditional<NCHW, float2, uint32_t>::type;      // SRC 2: two bytes (pixels kw, kw + 1)
+  using Raw = typename std::conditional<NCHW, float2, uint32_t>::type;      // SRC 2: look-up offsets of pixels kw, kw + 1
   Raw raw[3][4];
   auto load_raw = [&](int64_t tile) {
 #pragma unroll
@@ -100,10 +102,14 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
       } else if constexpr (SRC == 2) {
         // same K order as NCHW: slice s = channel, lane needs pixels (kh = t/2, kw = 2(t%2), +1) and kh + 2
         const uint8_t* xb = reinterpret_cast<const uint8_t*>(xin) + ((b * H + 4 * oy + (t >> 1)) * (int64_t)W + 4 * ox + 2 * (t & 1)) * 3;
+        // the two pixels are six contiguous bytes R G B R G B at an even offset: three 16-bit loads per patch row
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          raw[s][r] = (uint32_t)__ldg(xb + s) | ((uint32_t)__ldg(xb + 3 + s) << 8);
-          raw[s][r + 2] = (uint32_t)__ldg(xb + 6 * (int64_t)W + s) | ((uint32_t)__ldg(xb + 6 * (int64_t)W + 3 + s) << 8);
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint16_t* p = reinterpret_cast<const uint16_t*>(xb + kk * 6 * (int64_t)W);
+          const uint32_t rg = __ldg(p), br = __ldg(p + 1), gb = __ldg(p + 2);
+          raw[0][r + 2 * kk] = (rg & 255u) | ((br >> 8) << 8);            // R0, R1
+          raw[1][r + 2 * kk] = (rg >> 8) | ((gb & 255u) << 8);            // G0, G1
+          raw[2][r + 2 * kk] = (br & 255u) | ((gb >> 8) << 8);            // B0, B1
         }
       } else {
         // k = kh*12 + kw*3 + c; patch row kh = 12 contiguous elements at pixel (4oy + kh, 4ox)
@@ -127,7 +133,8 @@ stem_fused_kernel(const void* __restrict__ xin, T* __restrict__ y, const T* __re
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if constexpr (NCHW) a[s][i] = pack2<T>(raw[s][i].x, raw[s][i].y);
-        else if constexpr (SRC == 2) a[s][i] = (uint32_t)s_lut[s * 256 + (raw[s][i] & 255u)] | ((uint32_t)s_lut[s * 256 + (raw[s][i] >> 8)] << 16);
+        else if constexpr (SRC == 2)
+          a[s][i] = s_lut[(s * 256 + (raw[s][i] & 255u)) * 32 + lane] | (s_lut[(s * 256 + (raw[s][i] >> 8)) * 32 + lane] << 16);
         else a[s][i] = raw[s][i];
       }
     if (tile + warps < tiles) load_raw(tile + warps);
@@ -213,9 +220,17 @@ int stem_fused_src(int dtype, int src, const void* x, void* y, const void* w, co
   StemNorm nrm{};
   if (src == 2)
     for (int c = 0; c < 3; ++c) { nrm.mean[c] = mean3[c]; nrm.sd[c] = std3[c]; }
+  const size_t smem = src == 2 ? (size_t)3 * 256 * 32 * 4 : 0;
 #define GCV_STEM_LAUNCH(T, N)                                                                                              \
-  stem_fused_kernel<T, N><<<grid, ST_THREADS, 0, stream>>>(x, reinterpret_cast<T*>(y), reinterpret_cast<const T*>(w), bias, \
-                                                           ln_w, ln_b, eps, B, H, W, M, nrm)
+  do {                                                                                                                     \
+    if (N == 2) {                                                                                                          \
+      static unsigned long long attr_devs = 0;                                                                             \
+      if (first_on_device(attr_devs))                                                                                      \
+        cudaFuncSetAttribute(stem_fused_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+    }                                                                                                                      \
+    stem_fused_kernel<T, N><<<grid, ST_THREADS, smem, stream>>>(x, reinterpret_cast<T*>(y), reinterpret_cast<const T*>(w), \
+                                                                bias, ln_w, ln_b, eps, B, H, W, M, nrm);                   \
+  } while (0)
   if (dtype == GCV_BF16) {
     if (src == 1) GCV_STEM_LAUNCH(__nv_bfloat16, 1);
     else if (src == 2) GCV_STEM_LAUNCH(__nv_bfloat16, 2);

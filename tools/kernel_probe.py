@@ -112,7 +112,7 @@ if args.which == "top":
         if res:
             kw = dict(gamma=torch.rand(N, device=dev), residual=d, ldr=N)
         if ln:
-            st = torch.rand(M, 2, device=dev)
+            st = torch.rand(M, K // 32, 2, device=dev) + 1.0       # per-chunk partial sums: the statistics warps' path
             kw = dict(ln_stats=st, ln_colsum=torch.randn(N, device=dev), ln_eps=1e-6)
         L.gemm(a, w, d, M, N, K, bias=bias, act=act, **kw)
         note("gemm_tcgen05", f"M{M} N{N} K{K}" + ("+res" if res else "") + ("+ln" if ln else ""),
@@ -159,6 +159,27 @@ if args.which == "top":
     e3 = torch.empty(256 * 28 * 28, 64, device=dev, dtype=dt)
     L.conv3x3_c32(e2, e3, (torch.randn(64, 288, device=dev) / 17).to(dt), torch.zeros(64, device=dev), 1, L.ACT_RELU, True, 256, 56, 56)
     note("conv3x3_c32", "B256 H56 s1 pool", e2.numel() * 2.0 + e3.numel() * 2.0)
+    e4 = torch.empty(256 * 14 * 14, 128, device=dev, dtype=dt)
+    L.conv3x3_tc(e3, e4, (torch.randn(128, 576, device=dev) / 24).to(dt), torch.zeros(128, device=dev), 1, L.ACT_RELU, True,
+                 256, 28, 28, 64, 128)
+    note("conv3x3_tc", "B256 H28 C64 s1 pool", e3.numel() * 2.0 + e4.numel() * 2.0 + 128 * 576 * 2.0, 2.0 * 256 * 784 * 128 * 576)
+    e5 = torch.empty(256 * 7 * 7, 256, device=dev, dtype=dt)
+    L.conv3x3_tc(e4, e5, (torch.randn(256, 1152, device=dev) / 34).to(dt), torch.zeros(256, device=dev), 1, L.ACT_RELU, True,
+                 256, 14, 14, 128, 256)
+    note("conv3x3_tc", "B256 H14 C128 s1 pool", e4.numel() * 2.0 + e5.numel() * 2.0 + 256 * 1152 * 2.0, 2.0 * 256 * 196 * 256 * 1152)
+    d32 = torch.randn(256 * 56 * 56, 32, device=dev).to(dt)
+    img = torch.empty(256 * 224 * 224, 3, device=dev, dtype=dt)
+    L.convt2x2_mma(d32, img, (torch.randn(64, 32, device=dev) / 6).to(dt), torch.zeros(64, device=dev), L.ACT_RELU, 256, 56, 56,
+                   32, w2=(torch.randn(12, 16, device=dev) / 4).to(dt), b2=torch.zeros(12, device=dev))
+    note("convt2x2_mma", "B256 H56 C32 +tail", d32.numel() * 2.0 + img.numel() * 2.0)
+    u8 = torch.randint(0, 256, (256, 224, 224, 3), device=dev, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    L.stem_fused_u8(u8, tok, (torch.randn(96, 48, device=dev) / 7).to(dt), torch.zeros(96, device=dev), torch.ones(96, device=dev),
+                    torch.zeros(96, device=dev), 1e-6, 256, 224, 224, mean, std)
+    note("stem_fused", "B256 H224 u8", u8.numel() * 1.0 + tok.numel() * 2.0)
+    L.conv3x3_first_u8(u8, e1, torch.randn(16, 3, 3, 3, device=dev) / 5, torch.zeros(16, device=dev), 1, L.ACT_RELU, True, 256,
+                       224, 224, mean, std)
+    note("conv3x3_first", "B256 H224 s1 pool u8", u8.numel() * 1.0 + e1.numel() * 2.0)
     torch.cuda.synchronize()
     json.dump(order, open("gpurun_out/r2_top_order.json", "w"))
     print(len(order), "launches")
