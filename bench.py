@@ -538,8 +538,8 @@ def run_ours(args, rank, world, local_rank):
                          tensor_kernels={"achieved": tensor_tflops, "frac": tensor_tflops / peak_tf, "peak": peak_tf,
                                          "frac_of_sustained": tensor_tflops / peak_tf_sustained,
                                          "ms_per_step": t_ms, "kernels": list(tensor_kernels),
-                                         "def": "all launches of the tcgen05 GEMM + fused MLP of one step, algorithmic FLOPs / "
-                                                "CUDA-event time, against the burst peak"},
+                                         "def": "all launches of the tcgen05 kernels (GEMM, fused MLP, implicit-GEMM 3x3 conv) of one "
+                                                "step, algorithmic FLOPs / CUDA-event time, against the burst peak"},
                          whole_step={"achieved": step_tflops, "frac": step_tflops / peak_tf_sustained,
                                      "peak": peak_tf_sustained, "frac_of_burst": step_tflops / peak_tf,
                                      "def": "frames/s/GPU x 29.49 GFLOP contraction per frame, against the sustained peak"}),
