@@ -435,6 +435,33 @@ def test_video_scorer_uint8_ingest_matches_preprocess_then_forward(full_model):
         assert torch.equal(cls, c2) and torch.equal(val, v2), k
 
 
+def test_video_scorer_uint8_ingest_fp32_mode_uses_the_preprocess_kernel(full_model):
+    """fp32 compute mode: the uint8 crops go through gcv_preprocess_frames into the fp32 graph input (the exact-mode kernels
+    read pre-processed frames); same scores as preprocess_frame + forward, bit for bit."""
+    import numpy as np
+    from genconvit_b200.runtime import VideoScorer
+    from model import pred_func
+    from oracle.weights import synthetic_eps
+    n, fpv = 4, 2
+    rng = np.random.default_rng(6)
+    eps = synthetic_eps(n, 152).to(DEV)
+    full_model.set_compute_dtype("fp32")
+    try:
+        sc = VideoScorer(full_model, n, fpv, eps=eps, use_graph=True)
+        assert not sc.u8_fused
+        for _ in range(2):
+            frames = rng.integers(0, 256, size=(n, 224, 224, 3), dtype=np.uint8)
+            cls, val = sc.score(torch.from_numpy(frames).pin_memory())
+            full_model.model_vae.set_epsilon(eps)
+            try:
+                c2, v2 = pred_func.pred_videos(pred_func.preprocess_frame(frames), full_model, fpv)
+            finally:
+                full_model.model_vae.set_epsilon(None)
+            assert torch.equal(cls, c2) and torch.equal(val, v2)
+    finally:
+        full_model.set_compute_dtype("fp16")
+
+
 def L_launches():
     from genconvit_b200 import lib
     return lib.launches
