@@ -22,6 +22,7 @@ SOURCES = ["api.cu", "gemm_tcgen05.cu", "mlp_fused.cu", "gemm_simt.cu", "convnex
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += os.environ.get("GCV_NVCC_FLAGS", "").split()      # e.g. -DGCV_GEMM_WHATIF: the GEMM's timing-experiment switches
 
 
 def _deps():

@@ -44,6 +44,15 @@ constexpr int kStageSmem = kEpiWarps * kStageWarp;
 constexpr int kDynSmem = kCtrlSmem + kStageSmem + kVecSmem + 1024 + kTileSmem;   // +1024 alignment slack
 constexpr uint32_t kTmemCols = 512;
 
+// GCV_DEBUG what-if switches (timing experiments, results are garbage) only exist in builds with -DGCV_GEMM_WHATIF
+// (GCV_NVCC_FLAGS=-DGCV_GEMM_WHATIF python -m genconvit_b200.build): in the shipped kernel they were ~10 branches per
+// 32-column chunk of every epilogue warp.
+#ifdef GCV_GEMM_WHATIF
+constexpr bool kWhatIf = true;
+#else
+constexpr bool kWhatIf = false;
+#endif
+
 struct Params {
   int64_t M;
   int N, K;
@@ -111,6 +120,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   float* vec_gamma = vec_bias + kVecMaxN;
   const uint32_t tiles_base = smem_u32(smem_raw) + kCtrlSmem + kStageSmem + kVecSmem;
 
+  const int dbg = kWhatIf ? p.debug : 0;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform (see elect_one)
   const int lane = threadIdx.x & 31;
   const uint32_t b_rows = DUO ? (uint32_t)p.mma_n >> 1 : (uint32_t)p.mma_n;     // B rows this CTA stages per MMA
@@ -181,9 +191,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sa = tiles_base + stage * stage_bytes;
           if (!elect_one()) {
             // nothing to issue
-          } else if (p.debug >= 3 && p.debug <= 5) {
+          } else if (dbg >= 3 && dbg <= 5) {
             // mainloop experiments (results are garbage): 3 = no A loads, 4 = no B loads, 5 = no loads at all
-            const bool ldA = p.debug == 4, ldB = p.debug == 3;
+            const bool ldA = dbg == 4, ldB = dbg == 3;
             const uint32_t bytes = (ldA ? a_bytes : 0u) + (ldB ? b_bytes : 0u);
             if (!DUO || leader) mbar_expect_tx(fb, DUO ? 2 * bytes : bytes);
             if constexpr (DUO) {
@@ -399,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
         if (lane == 0) release_acc(as);
       }
-      if (p.debug == 1 || (p.debug >= 3 && p.debug <= 5)) {
+      if (dbg == 1 || (dbg >= 3 && dbg <= 5)) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && sub < chunks) release_acc(as);
@@ -407,15 +417,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int c = sub; c < chunks; c += 4) {
         const int n0 = n_blk * p.block_n + c * 32;
+        const bool full = n0 + 32 <= p.N;
 
         // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 576-thread CTA
         // leaves 96 registers per thread)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float v[16];
+          // this half's 16 columns of the per-column vectors (bias; layer scale / LayerNorm column sums), fetched from
+          // shared memory while the TMEM load is in flight: the asm statements around the load are memory barriers for
+          // the compiler, so left to itself it issues these loads after the wait and every FFMA2 stalls on them
+          float4 pb[4], pg[4];
           {
             uint32_t r[16];
             tc_ld16(t_row + c * 32 + h * 16, r);
+            if constexpr (MODE == 1 || MODE == 3 || MODE == 4) {
+              if (full) {
+                const int nh = n0 + h * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  pb[q] = *reinterpret_cast<const float4*>(vec_bias + nh + 4 * q);
+                  if constexpr (MODE != 1) pg[q] = *reinterpret_cast<const float4*>(vec_gamma + nh + 4 * q);
+                }
+              }
+            }
             tc_wait_ld();
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
@@ -425,7 +450,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();                                // hand the accumulator stage back to the MMA warp early
             if (lane == 0) release_acc(as);
           }
-          if (p.debug == 6) {                            // experiment: TMEM drain only
+          if (dbg == 6) {                            // experiment: TMEM drain only
             if (v[0] == 123.456f) *reinterpret_cast<float*>(my_stage) = v[5];
             continue;
           }
@@ -443,6 +468,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (elect_one()) tma_store_wait_read();      // tile: waited for as late as possible (after this chunk's TMEM load)
             __syncwarp();
           }
+          // interior chunks (all 32 columns inside N) take a copy of the loop without the per-8-column bounds checks
+          auto phase_a = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const int j = h * 2 + jj;
@@ -451,9 +479,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint4 q;
             if constexpr (MODE == 4) {
               // fc2 path: (acc + bias) * gamma + residual; columns past N (tile padding, N % 8 == 0) are never stored
-              if (n + 8 <= p.N) {
-                const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n), b1 = *reinterpret_cast<const float4*>(vec_bias + n + 4);
-                const float4 g0 = *reinterpret_cast<const float4*>(vec_gamma + n), g1 = *reinterpret_cast<const float4*>(vec_gamma + n + 4);
+              if (FULL || n + 8 <= p.N) {
+                const float4 b0 = FULL ? pb[2 * jj] : *reinterpret_cast<const float4*>(vec_bias + n);
+                const float4 b1 = FULL ? pb[2 * jj + 1] : *reinterpret_cast<const float4*>(vec_bias + n + 4);
+                const float4 g0 = FULL ? pg[2 * jj] : *reinterpret_cast<const float4*>(vec_gamma + n);
+                const float4 g1 = FULL ? pg[2 * jj + 1] : *reinterpret_cast<const float4*>(vec_gamma + n + 4);
                 const float2 r0 = unpack2<T>(res[j].x), r1 = unpack2<T>(res[j].y), r2 = unpack2<T>(res[j].z), r3 = unpack2<T>(res[j].w);
                 // (w + b) * g + r as w * g + (b * g + r): two FFMA2 per column pair
                 const float2 y0 = fma2(make_float2(w[0], w[1]), make_float2(g0.x, g0.y), fma2(make_float2(b0.x, b0.y), make_float2(g0.x, g0.y), r0));
@@ -464,18 +494,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               } else {
                 q = make_uint4(0u, 0u, 0u, 0u);
               }
-            } else if (gelu_only && n + 8 <= p.N) {
+            } else if (gelu_only && (FULL || n + 8 <= p.N)) {
               // fc1 fast path: bias + GELU in packed fp16 arithmetic
               if constexpr (MODE == 3)
-                q = ln_bias_gelu_pack8<T>(w, lnrs.x, lnrs.y, *reinterpret_cast<const float4*>(vec_gamma + n),
-                                          *reinterpret_cast<const float4*>(vec_gamma + n + 4),
-                                          *reinterpret_cast<const float4*>(vec_bias + n),
-                                          *reinterpret_cast<const float4*>(vec_bias + n + 4));
+                q = ln_bias_gelu_pack8<T>(w, lnrs.x, lnrs.y,
+                                          FULL ? pg[2 * jj] : *reinterpret_cast<const float4*>(vec_gamma + n),
+                                          FULL ? pg[2 * jj + 1] : *reinterpret_cast<const float4*>(vec_gamma + n + 4),
+                                          FULL ? pb[2 * jj] : *reinterpret_cast<const float4*>(vec_bias + n),
+                                          FULL ? pb[2 * jj + 1] : *reinterpret_cast<const float4*>(vec_bias + n + 4));
               else
-                q = bias_gelu_pack8<T>(w, *reinterpret_cast<const float4*>(vec_bias + n),
-                                       *reinterpret_cast<const float4*>(vec_bias + n + 4));
+                q = bias_gelu_pack8<T>(w, FULL ? pb[2 * jj] : *reinterpret_cast<const float4*>(vec_bias + n),
+                                       FULL ? pb[2 * jj + 1] : *reinterpret_cast<const float4*>(vec_bias + n + 4));
             } else {
-              if (n + 8 <= p.N) {
+              if (FULL || n + 8 <= p.N) {
                 if (p.vec_smem) {
                   if (ep.bias) {
                     const float4 b0 = *reinterpret_cast<const float4*>(vec_bias + n);
@@ -517,8 +548,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             *reinterpret_cast<uint4*>(my_stage + lane * kStageRow + ((j ^ ((lane >> 1) & 3)) << 4)) = q;
           }
+          };
+          if (full) phase_a(std::true_type{});
+          else phase_a(std::false_type{});
         }
-        if (!vec_ok || p.debug == 6) continue;
+        if (!vec_ok || dbg == 6) continue;
         if constexpr (MODE == 4) {
           if (c + 4 < chunks) fetch_residual(c + 4);     // in flight during phase B and the next chunk's TMEM loads
         }
@@ -526,7 +560,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // ---- phase B, TMA form: the 32 x 32 staged tile is one bulk tensor store (rows / columns past M / N are clipped)
           fence_proxy_async_smem();
           __syncwarp();
-          if (p.debug != 2 && p.debug != 7 && elect_one()) {
+          if (dbg != 2 && dbg != 7 && elect_one()) {
             tma_store_2d(&tmap_d, smem_u32(my_stage), n0, (int)m_warp);
             tma_store_commit();
           }
@@ -534,7 +568,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           continue;
         }
         __syncwarp();
-        if (p.debug == 2) { __syncwarp(); continue; }
+        if (dbg == 2) { __syncwarp(); continue; }
         // ---- phase B ----
         const int piece = lane & 3;
         const int n = n0 + piece * 8;
@@ -556,7 +590,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               } else {
                 off = mm * ep.ldd + n;
               }
-              if (p.debug != 7 || q.x == 0x12345678u)      // 7: everything but the global store itself
+              if (dbg != 7 || q.x == 0x12345678u)      // 7: everything but the global store itself
                 *reinterpret_cast<uint4*>(reinterpret_cast<T*>(D) + off) = q;
             }
           }
