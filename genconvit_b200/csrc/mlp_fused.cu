@@ -81,6 +81,13 @@ struct Cfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
+// GCV_FUSED_DEBUG what-if switches only exist in builds with -DGCV_GEMM_WHATIF (GCV_NVCC_FLAGS, see build.py)
+#ifdef GCV_GEMM_WHATIF
+constexpr bool kFWhatIf = true;
+#else
+constexpr bool kFWhatIf = false;
+#endif
+
 struct FParams {
   int64_t M;
   int tiles;
@@ -136,6 +143,7 @@ template <typename T, int C, bool LN>
 __global__ void __launch_bounds__(kFThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w1,
                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x, const FParams p) {
+  const int dbg = kFWhatIf ? p.debug : 0;
   using K = Cfg<C>;
   constexpr int NRING = K::RING > 0 ? K::RING : 1;
   extern __shared__ uint8_t smem_raw[];
@@ -444,7 +452,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int ob = ti % K::OBUF;
       const int64_t m_warp = (int64_t)tile * FM + q * 32;
-      if (p.debug == 4) {
+      if (dbg == 4) {
         mbar_wait(smem_u32(o_full + ob), (uint32_t)(ti / K::OBUF) & 1);
         tc_fence_before();
         __syncwarp();
@@ -494,7 +502,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           uint4* slot = reinterpret_cast<uint4*>(my_stage + lane * 64 + ((gq ^ ((lane >> 1) & 3)) << 4));
           float rr[8];
           {
-            const uint4 rq = p.debug == 2 ? make_uint4(0, 0, 0, 0) : *slot;      // residual row `lane`, columns n .. n+7
+            const uint4 rq = dbg == 2 ? make_uint4(0, 0, 0, 0) : *slot;      // residual row `lane`, columns n .. n+7
             float2 f;
             f = unpack2<T>(rq.x); rr[0] = f.x; rr[1] = f.y;
             f = unpack2<T>(rq.y); rr[2] = f.x; rr[3] = f.y;
@@ -517,7 +525,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + (lane >> 2);
           const int64_t mm = m_warp + r;
-          if (mm < p.M && p.debug != 3) {
+          if (mm < p.M && dbg != 3) {
             const uint4 pk = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((piece ^ ((r >> 1) & 3)) << 4));
             *reinterpret_cast<uint4*>(xg + mm * C + n0 + piece * 8) = pk;
           }
@@ -551,13 +559,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         if (ti != ln_ti) {
           if (ln_ti < 0) {
             const int64_t m = (int64_t)((int)blockIdx.x + ti * (int)gridDim.x) * FM + row;
-            if (m < p.M && p.debug != 5) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
+            if (m < p.M && dbg != 5) ln_row_load(p.ln_stats, m, C / 32, ln_raw);
           }
           lnrs = ln_row_finish(ln_raw, C / 32, C, p.ln_eps);
           lnrs.x *= 0.5f; lnrs.y *= 0.5f;
           ln_ti = ti;
           const int64_t mn = (int64_t)((int)blockIdx.x + (ti + 1) * (int)gridDim.x) * FM + row;
-          if (mn < p.M && p.debug != 5) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
+          if (mn < p.M && dbg != 5) ln_row_load(p.ln_stats, mn, C / 32, ln_raw);      // consumed at the next tile change
         }
       }
       const uint32_t n_use = (uint32_t)(g >> 1);
@@ -567,6 +575,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
       for (int hk = 0; hk < 2; ++hk) {
         const int kb = half * 2 + hk;        // K-block of the chunk = 32 hidden columns
         float v[32];
+        const float* bj = vec_b1 + j * FCH + kb * 32;
+        // the first 16 columns' bias / column-sum vectors are fetched while the TMEM load is in flight (the asm statements
+        // around it are compiler barriers: otherwise every shared-memory load is issued after the wait)
+        float4 pb[4], ps[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pb[e] = *reinterpret_cast<const float4*>(bj + 4 * e);
+          if constexpr (LN) ps[e] = *reinterpret_cast<const float4*>(bj + K::HC + 4 * e);
+        }
         {
           uint32_t r[32];
           tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * FCH + kb * 32, r);
@@ -579,9 +596,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(s_empty + b));
         }
-        const float* bj = vec_b1 + j * FCH + kb * 32;
         uint4 pk[4];
-        if (p.debug == 1) {
+        if (dbg == 1) {
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq)
             pk[gq] = make_uint4(__float_as_uint(v[gq * 8]), __float_as_uint(v[gq * 8 + 2]), __float_as_uint(v[gq * 8 + 4]), __float_as_uint(v[gq * 8 + 6]));
@@ -590,13 +606,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant
         for (int gq = 0; gq < 4; ++gq) {
           if constexpr (LN) {
             const float* sj = bj + K::HC;    // vec_s1 follows vec_b1
-            pk[gq] = ln_bias_gelu_pack8<T>(v + gq * 8, lnrs.x, lnrs.y, *reinterpret_cast<const float4*>(sj + gq * 8),
-                                           *reinterpret_cast<const float4*>(sj + gq * 8 + 4),
-                                           *reinterpret_cast<const float4*>(bj + gq * 8),
-                                           *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+            pk[gq] = ln_bias_gelu_pack8<T>(v + gq * 8, lnrs.x, lnrs.y,
+                                           gq < 2 ? ps[2 * gq] : *reinterpret_cast<const float4*>(sj + gq * 8),
+                                           gq < 2 ? ps[2 * gq + 1] : *reinterpret_cast<const float4*>(sj + gq * 8 + 4),
+                                           gq < 2 ? pb[2 * gq] : *reinterpret_cast<const float4*>(bj + gq * 8),
+                                           gq < 2 ? pb[2 * gq + 1] : *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
           } else {
-            pk[gq] = bias_gelu_pack8<T>(v + gq * 8, *reinterpret_cast<const float4*>(bj + gq * 8),
-                                        *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
+            pk[gq] = bias_gelu_pack8<T>(v + gq * 8, gq < 2 ? pb[2 * gq] : *reinterpret_cast<const float4*>(bj + gq * 8),
+                                        gq < 2 ? pb[2 * gq + 1] : *reinterpret_cast<const float4*>(bj + gq * 8 + 4));
           }
         }
         if (hk == 0) {                       // the single H buffer: fc2 of the previous chunk (g - 1) has retired;
