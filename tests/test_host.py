@@ -171,3 +171,14 @@ def test_audit_checkpoint_tool_reports_renamed_and_misshapen_keys(sd_ed, tmp_pat
     out = capsys.readouterr().out
     assert "wrapped {state_dict: ...}" in out and "~ backbone.stages.0.blocks.0.mlp.linear1.weight" in out
     assert "fc.weight: file (500, 1000), expected (500, 2000)" in out and "would FAIL" in out
+
+
+def test_u8_frames_wrapper_validates_its_input():
+    """engine.U8Frames: the raw-crop input form of the 16-bit forward (uint8 NHWC, contiguous); stands for NCHW frames."""
+    from genconvit_b200.engine import U8Frames
+    f = U8Frames(torch.zeros(2, 224, 224, 3, dtype=torch.uint8))
+    assert f.shape == (2, 3, 224, 224) and f.mean == (0.485, 0.456, 0.406) and not f.is_cuda
+    for bad in (torch.zeros(2, 224, 224, 3), torch.zeros(2, 3, 224, 224, dtype=torch.uint8),
+                torch.zeros(2, 224, 224, 6, dtype=torch.uint8)[..., ::2]):
+        with pytest.raises(ValueError):
+            U8Frames(bad)
