@@ -5,16 +5,17 @@
 // Replaces every nn.Linear / patchify-conv / im2col'd conv / k2s2 transposed conv
 // contraction of the GenConViT forward (see include/genconvit_b200.h, gcv_gemm).
 //
-// Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and
-//               B (block_n x 64) K-slices into a ring of 128B-swizzled smem stages
-//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=block_n, K=16)
-//               into one of two TMEM accumulator stages; tcgen05.commit frees smem
-//               stages and publishes finished accumulators
-//   warps 2..9  epilogue: tcgen05.ld of the fp32 accumulator (thread = row, 32
-//               columns per load), fused bias / activation / layer-scale+residual /
-//               VAE reparameterisation, 16-byte stores (rows or convT pixel shuffle)
-// The two TMEM stages let tile i's epilogue overlap tile i+1's MMAs.
+// Structure (one persistent CTA per SM, or a cta_group::2 pair of them; 640 threads):
+//   warp 0        TMA producer: cp.async.bulk.tensor 2D loads of the A (128x64) and B (block_n x 64) K-slices into a
+//                 ring of 128B-swizzled smem stages (whole warp runs the loop, one elected lane issues)
+//   warp 1        MMA issuer: tcgen05.mma (M=128 / 256 per pair, N=block_n, K=16) into a ring of 512/block_n TMEM
+//                 accumulator stages; tcgen05.commit frees smem stages and publishes finished accumulators
+//   warps 2..17   epilogue (4 per TMEM lane quarter): tcgen05.ld of the fp32 accumulator (thread = row, 2 x 16 columns
+//                 per 32-column chunk), fused bias / activation / folded LayerNorm / layer-scale+residual / VAE
+//                 reparameterisation, 16-bit result staged in smem and sent off as one TMA store per 32 x 32 piece
+//   warps 18..19  row statistics of the folded LayerNorm (fc1): reduce the per-chunk partial sums of a tile's 128 rows
+//                 one tile ahead of its epilogue (idle in the other modes)
+// The accumulator ring lets tile i's epilogue overlap the following tiles' MMAs.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -94,7 +95,7 @@ __device__ __noinline__ void epilogue_slow8(const gcv_epilogue& ep, int64_t m, i
 // the A rows folded in (gcv_epilogue.ln_stats: per-row rstd / mean from partial sums, column sums in vec_gamma);
 // 4 = staged, bias + layer-scale + residual only (ConvNeXt fc2): the residual rows are fetched a chunk ahead (the
 // first chunk before the accumulator wait), so their HBM latency is off the epilogue's critical path.  Separate instantiations keep each
-// epilogue within the 96 registers a 576-thread CTA leaves per thread.
+// epilogue within the 96 registers a 640-thread CTA leaves per thread.
 // DUO: the CTA pair of a 2-CTA cluster computes one 256 x block_n tile with cta_group::2 MMAs: each CTA stages its
 // own 128 rows of A and HALF of the B tile (so a stage is 16 KB + block_n/2 x 128 B instead of 16 KB + block_n x 128 B:
 // one third less shared-memory and L2 traffic per MAC, deeper pipeline), the leader CTA issues the MMAs, and each
@@ -419,7 +420,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n0 = n_blk * p.block_n + c * 32;
         const bool full = n0 + 32 <= p.N;
 
-        // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 576-thread CTA
+        // two 16-column TMEM loads per 32-column chunk: half the live registers of one x32 load (the 640-thread CTA
         // leaves 96 registers per thread)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
