@@ -724,3 +724,68 @@ def test_uint8_first_touch_kernels_equal_preprocess_then_fp32_kernels(dtype):
     L.stem_fused(x, a, ws, bs, lw, lb, 1e-6, B, H, W, True)
     L.stem_fused_u8(u8, b, ws, bs, lw, lb, 1e-6, B, H, W, mean, std)
     assert torch.equal(a, b)
+
+
+def _guarded(shape, dtype, pad=4096):
+    """An output tensor carved out of a larger buffer whose margins hold a sentinel (compute-sanitizer is not available on
+    the GPU pool: stray writes are caught by comparing the margins afterwards)."""
+    n = 1
+    for s in shape:
+        n *= s
+    buf = torch.full((n + 2 * pad,), 7.0, device=DEV, dtype=dtype)
+    return buf, buf[pad:pad + n].view(shape), pad
+
+
+def _margins_intact(buf, pad):
+    return bool((buf[:pad] == 7).all()) and bool((buf[-pad:] == 7).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_round2_kernels_do_not_write_outside_their_outputs(dtype):
+    """conv3x3_tc (ragged tiles: 20 x 12 and 7 x 7 maps, odd batch), convt2x2_mma (both forms), the uint8 first-touch kernels
+    and ln_patchify2 write exactly their output tensors."""
+    L = _lib()
+    from genconvit_b200.engine import _pack_conv3x3, _pack_convt
+    # conv3x3_tc: pooled, stride-2 (8 x 8 x 2 tile boxes with an odd image count), plain
+    for (B, H, W, ci, co, stride, pool) in ((3, 20, 12, 64, 128, 1, True), (3, 14, 14, 128, 256, 2, False), (1, 6, 10, 64, 64, 1, False)):
+        x = _rand(B, H, W, ci, dtype=dtype, seed=1)
+        wp = _pack_conv3x3(_rand(co, ci, 3, 3, seed=2, scale=(9 * ci) ** -0.5), DEV, dtype)
+        ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        if pool:
+            ho, wo = ho // 2, wo // 2
+        buf, out, pad = _guarded((B, ho, wo, co), dtype)
+        L.conv3x3_tc(x, out, wp, _rand(co, seed=3), stride, L.ACT_RELU, pool, B, H, W, ci, co)
+        torch.cuda.synchronize()
+        assert _margins_intact(buf, pad) and not bool((out == 7).all()), ("conv3x3_tc", B, H, W, ci, co, stride, pool)
+    # convt2x2_mma: 64 -> 32 and the fused tail
+    B, H, W = 3, 4, 12
+    p1, q1, _ = _pack_convt(_rand(64, 32, 2, 2, seed=4, scale=0.1), _rand(32, seed=5), DEV, dtype)
+    buf, out, pad = _guarded((B, 2 * H, 2 * W, 32), dtype)
+    L.convt2x2_mma(_rand(B * H * W, 64, dtype=dtype, seed=6), out, p1, q1, L.ACT_RELU, B, H, W, 64)
+    torch.cuda.synchronize()
+    assert _margins_intact(buf, pad)
+    p1, q1, _ = _pack_convt(_rand(32, 16, 2, 2, seed=7, scale=0.1), _rand(16, seed=8), DEV, dtype)
+    p2, q2, _ = _pack_convt(_rand(16, 3, 2, 2, seed=9, scale=0.2), _rand(3, seed=10), DEV, dtype)
+    buf, out, pad = _guarded((B, 4 * H, 4 * W, 3), dtype)
+    L.convt2x2_mma(_rand(B * H * W, 32, dtype=dtype, seed=11), out, p1, q1, L.ACT_LEAKY, B, H, W, 32, w2=p2, b2=q2)
+    torch.cuda.synchronize()
+    assert _margins_intact(buf, pad)
+    # uint8 first-touch kernels
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    B, H, W = 2, 32, 40
+    u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV)
+    buf, out, pad = _guarded((B, H // 2, W // 2, 16), dtype)
+    L.conv3x3_first_u8(u8, out, _rand(16, 3, 3, 3, seed=12, scale=0.2), _rand(16, seed=13), 1, L.ACT_RELU, True, B, H, W, mean, std)
+    torch.cuda.synchronize()
+    assert _margins_intact(buf, pad)
+    buf, out, pad = _guarded((B * (H // 4) * (W // 4), 96), dtype)
+    L.stem_fused_u8(u8, out, _rand(96, 48, seed=14, scale=0.15).to(dtype), _rand(96, seed=15), _rand(96, seed=16).abs() + 0.5,
+                    _rand(96, seed=17), 1e-6, B, H, W, mean, std)
+    torch.cuda.synchronize()
+    assert _margins_intact(buf, pad)
+    # ln_patchify2 (packed arithmetic), odd height: the last row is dropped
+    B, H, W, C = 3, 7, 6, 96
+    buf, out, pad = _guarded((B * (H // 2) * (W // 2), 4 * C), dtype)
+    L.ln_patchify2(_rand(B, H, W, C, dtype=dtype, seed=18), out, _rand(C, seed=19).abs() + 0.5, _rand(C, seed=20), 1e-6, B, H, W, C)
+    torch.cuda.synchronize()
+    assert _margins_intact(buf, pad) and bool(torch.isfinite(out.float()).all())
